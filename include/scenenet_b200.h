@@ -1,0 +1,199 @@
+/*
+ * scenenet_b200 — C ABI of the B200-native (sm_100a) SCENE-Net hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  Every
+ * buffer is DEVICE memory allocated by the caller (unless the name says `host`), every call
+ * is asynchronous on the `stream` handed in (a `cudaStream_t` passed as `void*`; NULL = the
+ * legacy default stream), nothing is allocated or freed by the library and there is no
+ * global mutable state, so calls are re-entrant across host threads and streams.
+ *
+ * Return value: 0 on success; SN_ERR_* (< 0) for argument errors; -(1000 + cudaError_t)
+ * for CUDA runtime errors at launch.
+ *
+ * The reference (dlavado/scene-net) is pure Python: there is no FFI in it to bind to.  Each
+ * entry point below therefore cites the reference *Python* lines whose arithmetic it
+ * replaces (paths relative to the reference root); INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add at exactly those lines.
+ *
+ * Layout conventions: voxel grids are [B,1,Z,X,Y] contiguous (Y fastest);
+ * GENEO kernels are [G,kz,kx,ky] contiguous; T = kz*kx*ky taps; cross-correlation with
+ * PyTorch 'same' zero padding: left pad (k-1)/2, right pad k-1-left.
+ */
+#ifndef SCENENET_B200_H
+#define SCENENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define SN_OK 0
+#define SN_ERR_BAD_ARG (-1)      /* null pointer, non-positive size, unknown enum          */
+#define SN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels are instantiated for    */
+#define SN_ERR_ALIGN (-3)        /* pointer not aligned as documented                      */
+#define SN_ERR_WORKSPACE (-4)    /* workspace smaller than sn_*_workspace_bytes() reports  */
+#define SN_ERR_CUDA_BASE (-1000) /* return = SN_ERR_CUDA_BASE - cudaError_t                */
+
+/* ---- dtypes of grid tensors crossing the boundary ------------------------------------ */
+#define SN_F32 0
+#define SN_F64 1
+
+/* ---- GENEO operator kinds (core/models/geneos/) -------------------------------------- */
+#define SN_KIND_CYLINDER_V1 0 /* cylinder.py:30-140   cylinder_kernel   params: radius, sigma                */
+#define SN_KIND_CYLINDER_V2 1 /* cylinder.py:146-176  cylinderv2        params: radius, sigma                */
+#define SN_KIND_CONE_V1 2     /* arrow.py:30-205      cone_kernel       params: apex, cone_inc, cone_radius, radius, sigma */
+#define SN_KIND_ARROW_V2 3    /* arrow.py:208-252     arrow             params: apex, cone_inc, cone_radius, radius, sigma */
+#define SN_KIND_NEGSPHERE_V1 4 /* neg_sphere.py:29-158 neg_sphere_kernel params: neg_factor, radius, sigma   */
+#define SN_KIND_NEGSPHERE_V2 5 /* neg_sphere.py:160-199 negSpherev2      params: neg_factor, radius, sigma   */
+
+#define SN_MAX_GENEOS 16
+#define SN_MAX_PARAM_PTRS 96 /* 16 operators x 5 params + 16 lambdas */
+#define SN_MAX_TAPS 4096     /* up to 16^3 */
+
+/*
+ * Host-side description of one observer (SceneNet / SCENE_Net instance,
+ * core/models/SCENE_Net.py:121-339).  `param_ptrs` (passed next to it) is a HOST array of
+ * DEVICE pointers to the model's 0-dim float32 parameters (nn.Parameter storage, used in
+ * place — no gather copy).  For operator g its parameters are
+ * param_ptrs[param_index[g] .. +n) in ALPHABETICAL name order (nn.ParameterDict order,
+ * SCENE_Net.py:83-89), its convex coefficient is param_ptrs[lambda_index[g]].
+ */
+typedef struct sn_model_desc {
+    int32_t n_geneos;                      /* G, channel order cy_*, cone_*, neg_* (SCENE_Net.py:264-275) */
+    int32_t kz, kx, ky;                    /* kernel_size (z, x, y)                                       */
+    int32_t n_param_ptrs;                  /* entries in param_ptrs                                       */
+    int32_t kind[SN_MAX_GENEOS];           /* SN_KIND_*                                                   */
+    int32_t param_index[SN_MAX_GENEOS];    /* first parameter of operator g in param_ptrs                 */
+    int32_t lambda_index[SN_MAX_GENEOS];   /* lambda_<g> in param_ptrs; -1 = no observer (GENEO_Layer use) */
+    int32_t lambda_sum_order[SN_MAX_GENEOS]; /* operator ids in lambdas_dict iteration order: the float32
+                                              left-to-right sum of SCENE_Net.py:331 is reproduced in it   */
+    int32_t last_lambda;                   /* operator id whose coefficient is 1 - sum(others); -1 = none */
+} sn_model_desc;
+
+/* library / ABI version, for the loader's sanity check */
+int sn_abi_version(void);
+/* writes a static NUL-terminated build string (arch, flags) */
+const char* sn_build_info(void);
+/* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
+int64_t sn_launch_count(void);
+
+/* ======================================================================================
+ * GENEO kernel synthesis — replaces GENEO_Layer.compute_kernel (SCENE_Net.py:103-106) and
+ * the compute_kernel methods of cylinder.py:85-103,162-176, arrow.py:170-205,228-252,
+ * neg_sphere.py:129-158,185-199.  One launch for all G operators.
+ *   K          [G,T] float32 out  — the G kernels (reference: geneo.kernel, float32)
+ *   lambda_eff [G]   float32 out  — effective convex coefficients (SCENE_Net.py:329-335);
+ *                                   the last one is (1 - sum(lambdas)) + lambda_last in float32
+ *   Kstar      [T]   float32 out  — sum_g lambda_eff[g] * K[g] (accumulated in float64): by
+ *                                   linearity of the convolution the observer's
+ *                                   sum_g lambda_g * conv3d(x, K_g) equals conv3d(x, Kstar)
+ *   write_last_lambda != 0: also stores lambda_eff[last] into the last-lambda parameter
+ *                                   (the side effect of SCENE_Net.py:333)
+ *   param_snapshot [n_param_ptrs] float32 out (NULL to skip) — the parameter values this
+ *                                   forward used (read before the last-lambda write), so a
+ *                                   later backward differentiates at the forward's point
+ * lambda_eff / Kstar may be NULL when desc->lambda_index[0] < 0 (bare GENEO kernels).
+ * ====================================================================================== */
+int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const* param_ptrs_host,
+                       float* K, float* lambda_eff, float* Kstar, float* param_snapshot,
+                       int write_last_lambda, void* stream);
+
+/* Jacobian^T of the synthesis: dparams[i] = sum_{g,t} dK[g,t] * dK_g[t]/dparam_i for every
+ * entry of param_ptrs (0 for apex and for lambdas).  Replaces autograd through the
+ * compute_kernel graphs cited above.  dK [G,T] float64, dparams [n_param_ptrs] float32 out. */
+int sn_geneo_synth_bwd(const sn_model_desc* desc, const float* const* param_ptrs_host,
+                       const double* dK, float* dparams, void* stream);
+
+/* Observer backward tail: from the tap gradient W[t] = sum_{b,v} G0[b,v] * xpad[b,v+t]
+ * (float64, produced by sn_scenenet_bwd) to the gradient of every parameter:
+ *   dK_g = lambda_eff[g] * W;  dlambda_g = <K_g - K_last, W> (g != last);  dparams via the
+ *   Jacobian^T above.  `scale` multiplies every output (1/world_size for DDP mean).
+ * Replaces autograd through SCENE_Net.py:324-337.  dparams [n_param_ptrs] float32 out.     */
+int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param_ptrs_host,
+                            const float* K, const float* lambda_eff, const double* W, double scale,
+                            float* dparams, void* stream);
+
+/* ======================================================================================
+ * Observer forward — replaces F.conv3d + convex combination + relu(tanh) of
+ * SceneNet.forward / SCENE_Net.forward (SCENE_Net.py:209-226, 322-339).
+ *   x     [B,1,Z,X,Y] float32          (use sn_cast_f64_to_f32 for the reference's float64 grids)
+ *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
+ *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
+ * x must be 16-byte aligned.
+ * ====================================================================================== */
+int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                    void* pred, int pred_dtype, void* stream);
+
+/* Observer backward, data part — replaces aten::convolution_backward (weight gradient) and
+ * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
+ *   G0 = dpred * (1 - pred^2) * [pred > 0];   W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t]
+ *   x [B,1,Z,X,Y] float32, pred / dpred in pred_dtype / dpred_dtype, W [T] float64 out.
+ *   ws: workspace of at least sn_scenenet_bwd_workspace_bytes(...) bytes, 16-byte aligned.
+ * Deterministic: fixed partition, fixed-order float64 reduction, no floating-point atomics. */
+int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
+int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
+                    int B, int Z, int X, int Y, int kz, int kx, int ky,
+                    double* W, void* ws, int64_t ws_bytes, void* stream);
+
+/* ======================================================================================
+ * elementwise helpers
+ * ====================================================================================== */
+/* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */
+int sn_cast_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
+/* prob_to_label (utils/voxelization.py:304-323) / SCENE_Net_Class.forward (SCENE_Net.py:465-466):
+ * out = (p >= tau) as 0/1, same dtype as p. */
+int sn_threshold(const void* p, int dtype, double tau, int64_t n, void* out, void* stream);
+
+/* ======================================================================================
+ * Voxelization — replaces eda.voxelize_ply (utils/pcd_processing.py:341-372 -> pyntcloud
+ * VoxelGrid.compute), Vox.hist_on_voxel / classes_on_voxel / reg_on_voxel
+ * (utils/voxelization.py:164-204, 207-241, 244-300) and eda.normalize_xyz
+ * (utils/pcd_processing.py:305-321).
+ *
+ * Points are float64 rows of `ld` doubles (x, y, z first; ld = 3 for an [N,3] array, ld = 4
+ * for the TS40K .npy rows x,y,z,label of core/datasets/ts40k.py:207), labels float64 with
+ * stride `label_ld` doubles (NULL = no labels).  Several clouds can be processed by one
+ * launch: cloud c owns points [offsets[c], offsets[c+1]) and grid slice c.
+ * ====================================================================================== */
+/* Step 1: per-cloud bounding box.  mnmx [C,6] float64 out = (xmin,ymin,zmin,xmax,ymax,zmax).
+ * The buffer is initialised by the call itself. */
+int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, double* mnmx, void* stream);
+
+/* Step 2: bin edges (np.linspace semantics: step=(hi-lo)/n rounded once, e[j]=fl(fl(j*step)+lo),
+ * e[n]=hi) after the regular-bounding-box (cube) adjustment.  nx,ny,nz: voxelgrid_dims.
+ * edges [C, (nx+1)+(ny+1)+(nz+1)] float64 out (x edges, then y, then z). */
+int sn_vox_edges(const double* mnmx, int n_clouds, int nx, int ny, int nz, double* edges, void* stream);
+
+/* Step 3: binning.  voxel = clip(searchsorted(edges, p, 'left') - 1, 0, n-1) per axis,
+ * lin = (vz*nx + vx)*ny + vy.  count / keep_count [C,nz,nx,ny] int32 and max_label
+ * [C,nz,nx,ny] (8 bytes per voxel; holds an order-preserving integer key until
+ * sn_vox_finalize decodes it to float64) are INITIALISED BY THE CALL; keep_count, max_label
+ * may be NULL.  keep [n_keep] float64 label values (device), lin_out [N] int32 (NULL to skip). */
+int sn_vox_bin(const double* pts, int ld, const double* labels, int label_ld, const int64_t* offsets,
+               int n_clouds, int64_t n_points_total, const double* edges, int nx, int ny, int nz,
+               const double* keep, int n_keep, int32_t* count, int32_t* keep_count, double* max_label,
+               int32_t* lin_out, void* stream);
+
+/* Step 4: finalize.  density = MinMax-normalised count per y column (float64, sklearn
+ * semantics), frac = keep/count (0 where empty), max_label keys -> float64 in place (0 where
+ * empty), occ = (count>0), occ_keep = (keep_count>0) as 0/1 in out_dtype.  Any output may be
+ * NULL.  ws: sn_vox_finalize_workspace_bytes() bytes (only needed when density != NULL). */
+int64_t sn_vox_finalize_workspace_bytes(int n_clouds, int ny);
+int sn_vox_finalize(const int32_t* count, const int32_t* keep_count, int n_clouds, int nx, int ny, int nz,
+                    double* density, double* frac, double* max_label, void* occ, void* occ_keep,
+                    int out_dtype, void* ws, void* stream);
+
+/* ======================================================================================
+ * measurement helper: FP32 FMA-pipe peak micro-benchmark (the roofline denominator that
+ * MEASURED_PEAKS.json lacks).  Runs `iters` dependent-chain FFMA rounds on every
+ * SM; the caller times it with CUDA events.  flops_out (host) receives the FLOPs issued. */
+int sn_fp32_peak_probe(float* sink, int iters, double* flops_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCENENET_B200_H */

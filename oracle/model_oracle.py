@@ -238,8 +238,8 @@ class OracleSceneNet:
 #            + FocalTverskyLoss (tversky_loss.py:81-95) + penalties (geneo_loss.py:36-71)
 # --------------------------------------------------------------------------------------
 def weight_target(y, weight_alpha=1.0, weight_epsilon=0.1):
-    freqs = torch.tensor(HIST_FREQS, dtype=torch.int64)
-    ranges = torch.tensor(HIST_RANGES, dtype=torch.float32)
+    freqs = torch.tensor(HIST_FREQS, dtype=torch.int64, device=y.device)
+    ranges = torch.tensor(HIST_RANGES, dtype=torch.float32, device=y.device)
     idx = torch.abs(torch.unsqueeze(y, -1) - ranges).argmin(dim=-1)
     hist = freqs[idx]
     fmin, fmax = freqs.min(), freqs.max()
@@ -248,9 +248,12 @@ def weight_target(y, weight_alpha=1.0, weight_epsilon=0.1):
     return w / torch.mean(w)
 
 
-def geneo_tversky_loss(pred, y, model: OracleSceneNet, weight_alpha=1.0, weight_epsilon=0.1, mse_weight=1.0,
-                       convex_weight=5.0, tversky_alpha=2.0, tversky_beta=1.0, focal_gamma=4.0,
-                       tversky_smooth=1e-6):
+def geneo_tversky_criterion(pred, y, lambdas, last, geneo_params, weight_alpha=1.0, weight_epsilon=0.1,
+                            mse_weight=1.0, convex_weight=5.0, tversky_alpha=2.0, tversky_beta=1.0, focal_gamma=4.0,
+                            tversky_smooth=1e-6):
+    """lambdas: mapping name -> 0-dim tensor in lambdas_dict order; last: name of the frozen one;
+    geneo_params: iterable of 0-dim tensors.  Works on any device (tests run it on CUDA tensors to
+    drive the CUDA model exactly like the reference's unchanged criterion would)."""
     w = weight_target(y, weight_alpha, weight_epsilon)
     dense = torch.mean(mse_weight * w * (y - pred) ** 2)
     tp = (pred * y).sum()
@@ -258,12 +261,15 @@ def geneo_tversky_loss(pred, y, model: OracleSceneNet, weight_alpha=1.0, weight_
     fn = (y * (1 - pred)).sum()
     tv = (tp + tversky_smooth) / (tp + tversky_alpha * fp + tversky_beta * fn + tversky_smooth)
     focal = (1 - tv) ** focal_gamma
-    lam = model.lambdas
-    last = model.last_lambda
-    cvx = convex_weight * (sum(torch.relu(-v) for k, v in lam.items() if k != last)
-                           + torch.relu(-(1 - sum(lam.values()) + lam[last])))
-    pos = convex_weight * sum(torch.relu(-t) for _, ps in model.geneos.values() for t in ps.values())
+    cvx = convex_weight * (sum(torch.relu(-v) for k, v in lambdas.items() if k != last)
+                           + torch.relu(-(1 - sum(lambdas.values()) + lambdas[last])))
+    pos = convex_weight * sum(torch.relu(-t) for t in geneo_params)
     return dense + focal + cvx + pos
+
+
+def geneo_tversky_loss(pred, y, model: "OracleSceneNet", **kw):
+    return geneo_tversky_criterion(pred, y, model.lambdas, model.last_lambda,
+                                   [t for _, ps in model.geneos.values() for t in ps.values()], **kw)
 
 
 # --------------------------------------------------------------------------------------

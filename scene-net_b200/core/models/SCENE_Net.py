@@ -1,0 +1,275 @@
+"""SCENE-Net observer modules — drop-in mirror of the reference's core/models/SCENE_Net.py
+(GENEO_Layer :56-113, SCENE_Net :121-226, SceneNet :229-339, SCENENetQuantile :347-415,
+SCENE_Net_Class :421-466): same constructors, same `forward(x)`, same module tree and
+`state_dict` keys (`geneos.<name>.geneo_params.<p>`, `lambdas_dict.lambda_<name>`), same
+accessors, same RNG draws at construction — but `forward` is three CUDA launches
+(kernel synthesis, [cast,] direct 3-D stencil + observer epilogue) and `backward` two
+(tap-gradient reduction, parameter Jacobian^T) instead of ~100 ATen ops + cuDNN conv3d.
+
+The criterion and the Lightning loop of the reference run unchanged on top: `forward`
+returns `pred` in the input dtype, and the accessors return the live nn.Parameters so the
+penalty terms of GENEO_Loss add their own autograd contributions.
+"""
+from __future__ import annotations
+
+from typing import Mapping
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._lib import KIND
+from .geneos import arrow, cylinder, neg_sphere
+from .geneos.GENEO_kernel_torch import GENEO_kernel_torch
+
+
+class _ObserverFunction(torch.autograd.Function):
+    """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, x, spec, write_last, grad_scale, *params):
+        K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
+        x32 = ops.cast_f32(x.detach())
+        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
+        ctx.spec = spec
+        ctx.grad_scale = grad_scale
+        ctx.save_for_backward(x32, pred, K, lam, snap)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        x32, pred, K, lam, snap = ctx.saved_tensors
+        W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size)
+        d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
+        grads = [d[i] if ctx.needs_input_grad[i + 4] else None for i in range(d.numel())]
+        return (None, None, None, None, *grads)
+
+
+###############################################################
+#                         GENEO Layer                         #
+###############################################################
+
+class GENEO_Layer(nn.Module):
+
+    def __init__(self, geneo_class: GENEO_kernel_torch, kernel_size: tuple = None, smart=False):
+        super(GENEO_Layer, self).__init__()
+        self.geneo_class = geneo_class
+        self.init_from_config(smart)
+        if kernel_size is not None:
+            self.kernel_size = kernel_size
+
+    def init_from_config(self, smart=False):
+        config = self.geneo_class.geneo_smart_config() if smart else self.geneo_class.geneo_random_config()
+        self.name = config['name']
+        self.kernel_size = config['kernel_size']
+        self.plot = config['plot']
+        params = {}
+        for pname, value in config['geneo_params'].items():
+            t = torch.as_tensor(value).detach().clone().to(torch.float)
+            params[pname] = nn.Parameter(t, requires_grad=pname not in config['non_trainable'])
+        self.geneo_params = nn.ParameterDict(params)  # plain dict -> keys sorted (reference behaviour)
+
+    def init_from_kwargs(self, kernel_size, kwargs):
+        self.kernel_size = kernel_size
+        self.name = 'GENEO'
+        self.plot = False
+        params = {p: nn.Parameter(torch.tensor(kwargs[p], dtype=torch.float)) for p in self.geneo_class.mandatory_parameters()}
+        self.geneo_params = nn.ParameterDict(params)
+
+    def compute_kernel(self) -> torch.Tensor:
+        """[1,kz,kx,ky] float64, differentiable w.r.t. geneo_params (SCENE_Net.py:103-106)."""
+        if self.geneo_class is neg_sphere.negSpherev2:
+            geneo = self.geneo_class(self.name, self.kernel_size, **self.geneo_params)
+        else:
+            geneo = self.geneo_class(self.name, self.kernel_size, plot=self.plot, **self.geneo_params)
+        kernel = geneo.kernel.to(dtype=torch.double)
+        return kernel.view(1, *kernel.shape)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        # dead code in the reference (SCENE_Net.py:108-113 reads an undefined self.device)
+        raise AttributeError("'GENEO_Layer' object has no attribute 'device'")
+
+
+###############################################################
+#                         SCENE-Nets                          #
+###############################################################
+
+class _SceneNetBase(nn.Module):
+    """Shared body of SCENE_Net (v1 kernels) and SceneNet (v2 kernels)."""
+
+    _classes: dict = {}
+
+    def _build(self, geneo_num, kernel_size, plot, lam_min, lam_max, lam_device=None):
+        self.sizes = {'cy': 1, 'cone': 1, 'neg': 1} if geneo_num is None else geneo_num
+        if kernel_size is not None:
+            self.kernel_size = kernel_size
+        self.geneos: Mapping[str, GENEO_Layer] = nn.ModuleDict()
+        for key in self.sizes:
+            if key in self._classes:
+                for i in range(self.sizes[key]):
+                    self.geneos[f'{key}_{i}'] = GENEO_Layer(self._classes[key], kernel_size=kernel_size)
+
+        # --- convex coefficients: same draws, same order as SCENE_Net.py:278-293 ---
+        num_lambdas = sum(self.sizes.values())
+        if lam_device is not None:  # SCENE_Net draws on its device's generator (SCENE_Net.py:177)
+            lambdas = (lam_max - lam_min) * torch.rand(num_lambdas, device=lam_device, dtype=torch.float) + lam_min
+        else:
+            lambdas = (lam_max - lam_min) * torch.rand(num_lambdas, dtype=torch.float) + lam_min
+        self.lambdas = [nn.Parameter(lamb) for lamb in lambdas]
+        self.lambda_names = [f'lambda_{key}_{i}' for key, val in self.sizes.items() for i in range(val)]
+        self.last_lambda = self.lambda_names[torch.randint(0, num_lambdas, (1,))[0]]
+        if plot:
+            print(f"last cvx_coeff: {self.last_lambda}")
+        lambdas_dict = dict(zip(self.lambda_names, self.lambdas))
+        lambdas_dict[self.last_lambda] = nn.Parameter(
+            1 - sum(lambdas_dict.values()) + lambdas_dict[self.last_lambda], requires_grad=False)
+        self.lambdas_dict = nn.ParameterDict(lambdas_dict)
+        #: multiply every parameter gradient by this (1/world_size gives DDP-mean semantics without a second pass)
+        self.grad_scale = 1.0
+        if plot:
+            print(f"Total Number of train params = {self.get_num_total_params()}")
+
+    # ---- accessors (SCENE_Net.py:194-207, 299-320) -------------------------------------
+    def get_geneo_nums(self):
+        return self.sizes
+
+    def get_cvx_coefficients(self):
+        return self.lambdas_dict
+
+    def get_num_total_params(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def get_model_parameters(self, detach=False):
+        if detach:
+            return {name: param.detach().clone() for name, param in self.named_parameters()}
+        return {name: param for name, param in self.named_parameters()}
+
+    def get_geneo_params(self):
+        return nn.ParameterDict(dict([(name.replace('.', '_'), p) for name, p in self.named_parameters() if 'lambda' not in name]))
+
+    def get_dict_parameters(self):
+        return dict([(n, param.data.item()) for n, param in self.named_parameters()])
+
+    def get_model_parameters_in_dict(self):
+        ddd = {}
+        for key, val in self.named_parameters():
+            key_split = key.split('.')
+            parameter_name = f"{key_split[-3]}.{key_split[-1]}" if 'geneo' in key else key_split[-1]
+            ddd[parameter_name] = val.data.item()
+        return ddd
+
+    # ---- the hot path -------------------------------------------------------------------
+    def _spec_and_params(self):
+        names = list(self.geneos.keys())
+        layers = [self.geneos[n] for n in names]
+        ks = {tuple(int(v) for v in l.kernel_size) for l in layers}
+        if len(ks) != 1:
+            raise ValueError(f"all GENEO kernels of an observer must share one kernel_size, got {ks}")
+        kinds = [KIND[l.geneo_class.kind_name] for l in layers]
+        params = []
+        for l in layers:
+            params.extend(l.geneo_params[p] for p in l.geneo_class.abi_params)
+        lam_keys = list(self.lambdas_dict.keys())  # iteration order of sum(self.lambdas_dict.values())
+        order = [names.index(k[len('lambda_'):]) for k in lam_keys]
+        params.extend(self.lambdas_dict[f'lambda_{n}'] for n in names)
+        spec = ops.ObserverSpec(kinds=kinds, kernel_size=ks.pop(), lambda_sum_order=order,
+                                last_lambda=names.index(self.last_lambda[len('lambda_'):]), observer=True)
+        return spec, params
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        spec, params = self._spec_and_params()
+        if not params[0].is_cuda:
+            raise RuntimeError("scenenet_b200: the model lives on the CPU; move it with .cuda() — the hot path is "
+                               "CUDA-only (no CPU fallback)")
+        if x.device != params[0].device:
+            raise RuntimeError(f"input on {x.device} but model on {params[0].device}")
+        # write_last=True reproduces the side effect of SCENE_Net.py:333 (last lambda <- 1 - sum(others)), in place
+        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), *params)
+
+
+class SCENE_Net(_SceneNetBase):
+    """v1 kernels (cylinder_kernel / cone_kernel / neg_sphere_kernel), lambdas ~ U(0, 0.6)."""
+
+    _classes = {'cy': cylinder.cylinder_kernel, 'cone': arrow.cone_kernel, 'neg': neg_sphere.neg_sphere_kernel}
+
+    def __init__(self, geneo_num=None, kernel_size=None, plot=False,
+                 device=torch.device('cuda' if torch.cuda.is_available() else 'cpu')):
+        super(SCENE_Net, self).__init__()
+        self.device = device
+        self._build(geneo_num, kernel_size, plot, lam_min=0.0, lam_max=0.6, lam_device=device)
+
+
+class SceneNet(_SceneNetBase):
+    """v2 kernels (cylinderv2 / arrow / negSpherev2), lambdas ~ U(-2/G, 1/G)."""
+
+    _classes = {'cy': cylinder.cylinderv2, 'cone': arrow.arrow, 'neg': neg_sphere.negSpherev2}
+
+    def __init__(self, geneo_num=None, kernel_size=None, plot=False):
+        super(SceneNet, self).__init__()
+        sizes = {'cy': 1, 'cone': 1, 'neg': 1} if geneo_num is None else geneo_num
+        n = sum(sizes.values())
+        self._build(geneo_num, kernel_size, plot, lam_min=-2 / n, lam_max=1 / n)
+
+
+###############################################################
+#                     SCENE-Net Quantile                      #
+###############################################################
+class SCENENetQuantile(nn.Module):
+    """One SCENE_Net per quantile on the same input (SCENE_Net.py:347-415)."""
+
+    def __init__(self, geneo_num=None, kernel_size=None, qs=torch.tensor([0.1, 0.5, 0.9]), plot=False, model_path=None,
+                 device=torch.device('cuda' if torch.cuda.is_available() else 'cpu')) -> None:
+        super(SCENENetQuantile, self).__init__()
+        if model_path is not None:
+            raise NotImplementedError("legacy .pt checkpoints (SCENE_Net.py:18-49) are outside the hot path")
+        self.scnets = nn.ModuleList([SCENE_Net(geneo_num, kernel_size, plot) for _ in range(len(qs))]).to(device)
+        self.qs = qs
+        self.device = device
+
+    def get_num_total_params(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def get_dict_parameters(self):
+        return dict([(n, param.data.item()) for n, param in self.named_parameters()])
+
+    def get_cvx_coefficients(self):
+        return [scnet.get_cvx_coefficients() for scnet in self.scnets]
+
+    def get_geneo_params(self):
+        return [scnet.get_geneo_params() for scnet in self.scnets]
+
+    def forward(self, x: torch.Tensor):
+        return torch.cat([net(x).to(torch.float32) for net in self.scnets], dim=1)
+
+
+class SCENE_Net_Class(nn.Module):
+    """Thresholded classifier (SCENE_Net.py:421-466): (gnet(x) >= tau) as 0/1 in x.dtype."""
+
+    def __init__(self, geneo_num=None, plot=True, gnet_requires_grad=True, gnet_model_path=None):
+        super().__init__()
+        if gnet_model_path is not None:
+            raise NotImplementedError("legacy checkpoints are outside the hot path")
+        self.gnet = SCENE_Net(geneo_num)
+        if not gnet_requires_grad:
+            for param in self.gnet.parameters():
+                param.requires_grad = False
+        tau_min, tau_max = 0.2, 0.6
+        self.tau = nn.Parameter((tau_max - tau_min) * torch.rand(1, dtype=torch.float)[0])
+
+    def get_threshold(self):
+        return self.tau
+
+    def get_geneo_nums(self):
+        return self.gnet.sizes
+
+    def get_cvx_coefficients(self):
+        return self.gnet.lambdas_dict
+
+    def get_geneo_params(self):
+        return nn.ParameterDict(dict([(name.replace('.', '_'), p) for name, p in self.gnet.named_parameters() if 'lambda' not in name]))
+
+    def get_dict_parameters(self):
+        return dict([(n, param.data.item()) for n, param in self.gnet.named_parameters()])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.threshold(self.gnet(x), float(self.tau)).to(x.dtype)

@@ -1,0 +1,311 @@
+// Observer backward, data part: the tap gradient
+//     W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t],   G0 = dpred * (1 - pred^2) * [pred > 0]
+// Replaces aten::convolution_backward (weight gradient) + the relu/tanh backward that
+// autograd runs for SCENE_Net.py:325-337.  W is ONE T-vector (not G of them): the per-
+// operator gradients are lambda_g * W (synth.cu::sn_scenenet_param_grads).
+//
+// Persistent CTAs walk 8 x TX x TY voxel tiles (static round-robin => deterministic).  Per
+// tile: x halo by one TMA load, G0 computed on the fly from pred/dpred into shared memory.
+// Warp w of a CTA owns tap group (dx, z-chunk) for the whole kernel and keeps its C*KY
+// accumulators in registers; its lanes sweep the tile's 8x4 micro-tiles.  At the end every
+// warp reduces its accumulators across lanes in float64 and writes one partial row; a second
+// tiny kernel sums the rows in fixed order (no floating-point atomics anywhere).
+#include "stencil_common.cuh"
+#include "tma_host.cuh"
+
+namespace sn {
+
+constexpr int kBwdMaxWarps = 8;
+
+template <int KY, int CS>
+__device__ __forceinline__ void bwd_chunk(float (&acc)[Geo<KY>::C * KY], const float* __restrict__ sxp, int zstride,
+                                          const float* __restrict__ sgp, int gzstride) {
+    constexpr int WN = Geo<KY>::WN;
+    float g[kRZ][4];
+    bool any = false;
+#pragma unroll
+    for (int z = 0; z < kRZ; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(sgp + z * gzstride);
+        g[z][0] = v.x; g[z][1] = v.y; g[z][2] = v.z; g[z][3] = v.w;
+        any |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+    }
+    (void)any;
+#pragma unroll
+    for (int zi = 0; zi < kRZ + CS - 1; ++zi) {
+        float win[WN];
+#pragma unroll
+        for (int i = 0; i < WN / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(sxp + zi * zstride + 4 * i);
+            win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int dzl = 0; dzl < CS; ++dzl) {
+            const int zo = zi - dzl;
+            if (zo >= 0 && zo < kRZ) {
+#pragma unroll
+                for (int dy = 0; dy < KY; ++dy) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        acc[dzl * KY + dy] = fmaf(g[zo][r], win[r + dy], acc[dzl * KY + dy]);
+                }
+            }
+        }
+    }
+}
+
+template <int KY, int CS>
+struct BwdChunkSwitch {
+    __device__ static __forceinline__ void run(int cs, float (&acc)[Geo<KY>::C * KY], const float* sxp, int zstride,
+                                               const float* sgp, int gzstride) {
+        if (cs == CS)
+            bwd_chunk<KY, CS>(acc, sxp, zstride, sgp, gzstride);
+        else
+            BwdChunkSwitch<KY, CS - 1>::run(cs, acc, sxp, zstride, sgp, gzstride);
+    }
+};
+template <int KY>
+struct BwdChunkSwitch<KY, 0> {
+    __device__ static __forceinline__ void run(int, float (&)[Geo<KY>::C * KY], const float*, int, const float*, int) {}
+};
+
+template <int KY, int TYT>
+__global__ void __launch_bounds__(kBwdMaxWarps * 32, 2)
+stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int C = Geo<KY>::C;
+    constexpr int NACC = C * KY;
+    constexpr int TY = TYT * 4, TX = kStencilThreads / TYT;
+    constexpr int MICRO = TX * TYT;  // micro-tiles per CTA tile (z extent of a tile == kRZ)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const int halo_floats = g.HZ * g.HX * g.WS;
+    float* sx = reinterpret_cast<float*>(smem_raw);
+    float* sg = sx + ((halo_floats + 31) & ~31);  // [kRZ][TX][TY]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sg + kRZ * TX * TY);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int combo = blockIdx.y * p.combos_per_cta + warp;
+    const bool active = combo < p.ncombos;
+    const int dx = active ? combo / g.nchunks : 0, ch = active ? combo % g.nchunks : 0;
+    const int cs = min(C, p.kz - ch * C);
+
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+    if (p.use_tma && tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    uint32_t phase = 0;
+    const int zstride = g.HX * g.WS, gzstride = TX * TY;
+    const bool vec = (p.Y & 3) == 0;
+
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        int b, z0, x0, y0;
+        decode_tile(tile, g, b, z0, x0, y0);
+        __syncthreads();  // everyone is done with the previous tile's shared memory
+        if (p.use_tma) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, (uint32_t)halo_floats * 4u);
+                tma_load_4d(sx, &tmap, bar, y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+            }
+        } else {
+            load_halo_plain(sx, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, nthreads);
+        }
+        // G0 tile: 4 consecutive y per thread per step
+        for (int i = tid; i < kRZ * TX * TYT; i += nthreads) {
+            const int y4 = i % TYT, xx = (i / TYT) % TX, zz = i / (TYT * TX);
+            const int gz = z0 + zz, gx = x0 + xx, gy = y0 + 4 * y4;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gz < p.Z && gx < p.X && gy < p.Y) {
+                const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
+                float pv[4], dv[4];
+                if (vec) {
+                    if (p.pred_f64) {
+                        const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[0];
+                        const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[1];
+                        pv[0] = (float)a.x; pv[1] = (float)a.y; pv[2] = (float)c.x; pv[3] = (float)c.y;
+                    } else {
+                        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pred) + idx);
+                        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
+                    }
+                    if (p.dpred_f64) {
+                        const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[0];
+                        const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[1];
+                        dv[0] = (float)a.x; dv[1] = (float)a.y; dv[2] = (float)c.x; dv[3] = (float)c.y;
+                    } else {
+                        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dpred) + idx);
+                        dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool ok = gy + r < p.Y;
+                        pv[r] = !ok ? 0.f
+                                    : (p.pred_f64 ? (float)reinterpret_cast<const double*>(p.pred)[idx + r]
+                                                  : reinterpret_cast<const float*>(p.pred)[idx + r]);
+                        dv[r] = !ok ? 0.f
+                                    : (p.dpred_f64 ? (float)reinterpret_cast<const double*>(p.dpred)[idx + r]
+                                                   : reinterpret_cast<const float*>(p.dpred)[idx + r]);
+                    }
+                }
+                o = make_float4(g0_of(pv[0], dv[0]), g0_of(pv[1], dv[1]), g0_of(pv[2], dv[2]), g0_of(pv[3], dv[3]));
+            }
+            *reinterpret_cast<float4*>(sg + (zz * TX + xx) * TY + 4 * y4) = o;
+        }
+        __syncthreads();
+        if (p.use_tma) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        if (active) {
+            for (int m = lane; m < MICRO; m += 32) {
+                const int tyi = m % TYT, txi = m / TYT;
+                const float* sxp = sx + (ch * C) * zstride + (txi + dx) * g.WS + 4 * tyi;
+                const float* sgp = sg + txi * TY + 4 * tyi;
+                if (cs == C)
+                    bwd_chunk<KY, C>(acc, sxp, zstride, sgp, gzstride);
+                else
+                    BwdChunkSwitch<KY, C - 1>::run(cs, acc, sxp, zstride, sgp, gzstride);
+            }
+        }
+    }
+
+    // cross-lane reduction in float64, one partial row per CTA column (blockIdx.x)
+    if (active) {
+        double* row = p.partial + (size_t)blockIdx.x * p.TP;
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+            const double s = warp_sum((double)acc[i]);
+            const int dzl = i / KY, dy = i % KY;
+            if (lane == 0 && dzl < cs) row[((ch * C + dzl) * p.kx + dx) * KY + dy] = s;
+        }
+    }
+}
+
+// W[t] = sum over partial rows, fixed order
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ partial, int rows, int TP, int T,
+                                                              double* __restrict__ W) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+        s0 += partial[(size_t)r * TP + t];
+        s1 += partial[(size_t)(r + 1) * TP + t];
+        s2 += partial[(size_t)(r + 2) * TP + t];
+        s3 += partial[(size_t)(r + 3) * TP + t];
+    }
+    for (; r < rows; ++r) s0 += partial[(size_t)r * TP + t];
+    W[t] = (s0 + s1) + (s2 + s3);
+}
+
+struct BwdPlan {
+    int grid_x, grid_y, combos_per_cta, ncombos, TP;
+    size_t smem;
+};
+
+template <int KY, int TYT>
+static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
+    const TileGeo g = make_geo<KY, TYT>(B, Z, X, Y, kz, kx);
+    BwdPlan pl;
+    pl.ncombos = kx * g.nchunks;
+    pl.grid_y = ceil_div(pl.ncombos, kBwdMaxWarps);
+    pl.combos_per_cta = ceil_div(pl.ncombos, pl.grid_y);
+    const int halo_floats = g.HZ * g.HX * g.WS;
+    pl.smem = (size_t)(((halo_floats + 31) & ~31) + kRZ * g.TX * g.TY) * 4 + 16;
+    int per_sm = (int)((227 * 1024) / (pl.smem + 1024));
+    const int thr = pl.combos_per_cta * 32;
+    per_sm = min(per_sm, 2048 / thr);
+    per_sm = min(per_sm, 65536 / (thr * 128));
+    per_sm = max(1, min(per_sm, 4));
+    int gx = kNumSMs * per_sm / pl.grid_y;
+    gx = max(1, min(gx, g.ntiles));
+    pl.grid_x = gx;
+    pl.TP = (kz * kx * KY + 31) & ~31;
+    return pl;
+}
+
+template <int KY, int TYT>
+static int launch_bwd(BwdParams p, double* W, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    const BwdPlan pl = plan_bwd<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    if (pl.smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
+    if ((int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    CUtensorMap tmap;
+    p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
+    p.partial = reinterpret_cast<double*>(ws);
+    p.ncombos = pl.ncombos;
+    p.combos_per_cta = pl.combos_per_cta;
+    p.TP = pl.TP;
+    auto kern = stencil_bwd_kernel<KY, TYT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+    kern<<<dim3(pl.grid_x, pl.grid_y), pl.combos_per_cta * 32, pl.smem, stream>>>(p, tmap);
+    SN_LAUNCH_CHECK();
+    const int T = p.kz * p.kx * KY;
+    reduce_partials_kernel<<<ceil_div(T, 128), 128, 0, stream>>>(p.partial, pl.grid_x, pl.TP, T, W);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+int stencil_bwd_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream);  // stencil_generic.cu
+
+template <int KY>
+static int dispatch_bwd_ty(const BwdParams& p, double* W, void* ws, int64_t wsb, cudaStream_t s) {
+    return p.Y > 32 ? launch_bwd<KY, 16>(p, W, ws, wsb, s) : launch_bwd<KY, 8>(p, W, ws, wsb, s);
+}
+template <int KY>
+static int64_t ws_bytes_ty(int B, int Z, int X, int Y, int kz, int kx) {
+    const BwdPlan pl = Y > 32 ? plan_bwd<KY, 16>(B, Z, X, Y, kz, kx) : plan_bwd<KY, 8>(B, Z, X, Y, kz, kx);
+    return (int64_t)pl.grid_x * pl.TP * 8;
+}
+
+}  // namespace sn
+
+extern "C" int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    switch (ky) {
+        case 3: return sn::ws_bytes_ty<3>(B, Z, X, Y, kz, kx);
+        case 5: return sn::ws_bytes_ty<5>(B, Z, X, Y, kz, kx);
+        case 6: return sn::ws_bytes_ty<6>(B, Z, X, Y, kz, kx);
+        case 7: return sn::ws_bytes_ty<7>(B, Z, X, Y, kz, kx);
+        case 9: return sn::ws_bytes_ty<9>(B, Z, X, Y, kz, kx);
+        case 11: return sn::ws_bytes_ty<11>(B, Z, X, Y, kz, kx);
+        case 13: return sn::ws_bytes_ty<13>(B, Z, X, Y, kz, kx);
+        case 15: return sn::ws_bytes_ty<15>(B, Z, X, Y, kz, kx);
+        default: return 256;  // generic path needs no workspace
+    }
+}
+
+extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
+                               int B, int Z, int X, int Y, int kz, int kx, int ky, double* W, void* ws, int64_t ws_bytes,
+                               void* stream) {
+    if (!x || !pred || !dpred || !W) return SN_ERR_BAD_ARG;
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    if ((pred_dtype != SN_F32 && pred_dtype != SN_F64) || (dpred_dtype != SN_F32 && dpred_dtype != SN_F64))
+        return SN_ERR_BAD_ARG;
+    if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
+    if (ws && ((uintptr_t)ws & 15)) return SN_ERR_ALIGN;
+    sn::BwdParams p{};
+    p.x = x; p.pred = pred; p.dpred = dpred;
+    p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx;
+    p.pred_f64 = pred_dtype == SN_F64; p.dpred_f64 = dpred_dtype == SN_F64;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (!ws && ky != 0) ws_bytes = 0;
+    switch (ky) {
+        case 3: rc = sn::dispatch_bwd_ty<3>(p, W, ws, ws_bytes, s); break;
+        case 5: rc = sn::dispatch_bwd_ty<5>(p, W, ws, ws_bytes, s); break;
+        case 6: rc = sn::dispatch_bwd_ty<6>(p, W, ws, ws_bytes, s); break;
+        case 7: rc = sn::dispatch_bwd_ty<7>(p, W, ws, ws_bytes, s); break;
+        case 9: rc = sn::dispatch_bwd_ty<9>(p, W, ws, ws_bytes, s); break;
+        case 11: rc = sn::dispatch_bwd_ty<11>(p, W, ws, ws_bytes, s); break;
+        case 13: rc = sn::dispatch_bwd_ty<13>(p, W, ws, ws_bytes, s); break;
+        case 15: rc = sn::dispatch_bwd_ty<15>(p, W, ws, ws_bytes, s); break;
+        default: rc = SN_ERR_UNSUPPORTED; break;
+    }
+    if (rc == SN_ERR_UNSUPPORTED) rc = sn::stencil_bwd_generic(p, ky, W, s);
+    return rc;
+}

@@ -1,0 +1,104 @@
+// Shared pieces of the direct 3-D stencil kernels (forward observer + tap-gradient backward).
+//
+// Register blocking: every thread owns an RZ x 4 micro-tile (RZ voxels along z, 4 along the
+// contiguous y axis).  The tap loop is split into runtime loops over dx and z-chunks and a
+// fully unrolled inner body over (C z-taps) x (KY y-taps): one 16-byte shared-memory window
+// load feeds up to C*KY*4 FFMAs, so the kernels are bound by the FP32 pipe, not by shared
+// memory or HBM.
+#pragma once
+#include "common.cuh"
+
+namespace sn {
+
+constexpr int kRZ = 8;           // z extent of a micro-tile == z extent of a CTA tile
+constexpr int kStencilThreads = 128;
+
+// z-chunk (taps held in registers at once) per compile-time KY: C*KY <= 48 registers
+__host__ __device__ constexpr int cmax_for(int ky) {
+    return ky <= 5 ? 9 : (ky == 6 ? 8 : (ky == 7 ? 6 : (ky <= 9 ? 5 : (ky <= 11 ? 4 : 3))));
+}
+__host__ __device__ constexpr int round4(int v) { return (v + 3) & ~3; }
+
+template <int KY>
+struct Geo {
+    static constexpr int C = cmax_for(KY);
+    static constexpr int CKP = round4(C * KY);  // taps of one (dx, chunk) slot, padded for 16-byte loads
+    static constexpr int WN = round4(KY + 3);   // window floats a thread reads per input row
+};
+
+struct FwdParams {
+    const float* x;
+    const float* Kstar;
+    void* pred;
+    int B, Z, X, Y, kz, kx;
+    int out_f64, use_tma;
+};
+
+struct BwdParams {
+    const float* x;
+    const void* pred;
+    const void* dpred;
+    double* partial;  // [gridDim.x][TP]
+    int B, Z, X, Y, kz, kx;
+    int pred_f64, dpred_f64, use_tma;
+    int ncombos, combos_per_cta, TP;
+};
+
+__device__ __forceinline__ float g0_of(float p, float d) { return p > 0.f ? d * (1.f - p * p) : 0.f; }
+
+// tile geometry shared by host and device
+struct TileGeo {
+    int TY, TX;          // CTA tile extent in y, x (z extent is kRZ)
+    int HZ, HX, WS;      // halo tile extents (rows, rows, padded row length in floats)
+    int tiles_z, tiles_x, tiles_y, ntiles;
+    int nchunks;         // ceil(kz / C)
+    int plz, plx, ply;   // left pads
+};
+
+template <int KY, int TYT>
+__host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, int kx) {
+    TileGeo g;
+    g.TY = TYT * 4;
+    g.TX = kStencilThreads / TYT;
+    g.HZ = kRZ + kz - 1;
+    g.HX = g.TX + kx - 1;
+    g.WS = round4(g.TY + KY - 1);
+    g.tiles_z = ceil_div(Z, kRZ);
+    g.tiles_x = ceil_div(X, g.TX);
+    g.tiles_y = ceil_div(Y, g.TY);
+    g.ntiles = B * g.tiles_z * g.tiles_x * g.tiles_y;
+    g.nchunks = ceil_div(kz, Geo<KY>::C);
+    g.plz = pad_left(kz);
+    g.plx = pad_left(kx);
+    g.ply = pad_left(KY);
+    return g;
+}
+
+// plain-load fallback for the halo tile (odd Y, unaligned base, no driver entry point)
+__device__ __forceinline__ void load_halo_plain(float* __restrict__ sx, const float* __restrict__ x, const TileGeo& g,
+                                                int Z, int X, int Y, int b, int z0, int x0, int y0, int nthreads) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    for (int r = warp; r < g.HZ * g.HX; r += nwarps) {
+        const int gz = z0 - g.plz + r / g.HX, gx = x0 - g.plx + r % g.HX;
+        const bool row_ok = gz >= 0 && gz < Z && gx >= 0 && gx < X;
+        const float* src = x + (((size_t)b * Z + (row_ok ? gz : 0)) * X + (row_ok ? gx : 0)) * Y;
+        for (int c = lane; c < g.WS; c += 32) {
+            const int gy = y0 - g.ply + c;
+            sx[r * g.WS + c] = (row_ok && gy >= 0 && gy < Y) ? __ldg(src + gy) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void decode_tile(int tile, const TileGeo& g, int& b, int& z0, int& x0, int& y0) {
+    const int ty = tile % g.tiles_y;
+    tile /= g.tiles_y;
+    const int tx = tile % g.tiles_x;
+    tile /= g.tiles_x;
+    const int tz = tile % g.tiles_z;
+    b = tile / g.tiles_z;
+    z0 = tz * kRZ;
+    x0 = tx * g.TX;
+    y0 = ty * g.TY;
+}
+
+}  // namespace sn

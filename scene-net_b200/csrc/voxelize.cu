@@ -1,0 +1,358 @@
+// Point-cloud voxelization: bounding box -> linspace edges -> searchsorted binning with
+// warp-aggregated atomics -> count / keep-count / max-label grids -> density / fraction /
+// occupancy.  Replaces (paths relative to the reference root)
+//   utils/pcd_processing.py:341-372 (eda.voxelize_ply -> pyntcloud==0.1.6 VoxelGrid.compute)
+//   utils/voxelization.py:164-204, 207-241, 244-300 (hist_on_voxel, classes_on_voxel, reg_on_voxel)
+//   utils/pcd_processing.py:305-321 (normalize_xyz = sklearn MinMaxScaler per y column)
+//   core/datasets/torch_transforms.py:33-40 (ToFullDense.densify)
+//
+// Everything that decides a voxel index is float64 with explicitly rounded operations
+// (__dmul_rn/__dadd_rn/__ddiv_rn: no FMA contraction), because TS40K coordinates are UTM
+// (~5e5, ~4.6e6 m) and a 1-ulp edge difference moves points across voxels.
+// HBM-bound: 24 B/point (bounding box) + 32 B/point (bin) + the grid passes.
+#include <math.h>
+#include "common.cuh"
+
+namespace sn {
+
+constexpr int kVoxThreads = 256;
+
+__device__ __forceinline__ void atomic_min_f64(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (v > __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+// monotone map double -> int64 (an involution), so atomicMax on integers orders doubles
+__device__ __forceinline__ long long f64_key(double d) {
+    const long long b = __double_as_longlong(d);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double key_f64(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+
+// ------------------------------------------------------------------ step 1: bounding boxes
+__global__ void minmax_init_kernel(double* mnmx, int n_clouds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_clouds * 6) mnmx[i] = (i % 6) < 3 ? INFINITY : -INFINITY;
+}
+
+__global__ void __launch_bounds__(kVoxThreads)
+minmax_kernel(const double* __restrict__ pts, int ld, const long long* __restrict__ offsets, double* __restrict__ mnmx) {
+    __shared__ double red[6][kVoxThreads / 32];
+    const int c = blockIdx.y;
+    const long long beg = offsets[c], end = offsets[c + 1];
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const bool vec4 = (ld == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
+    for (long long i = beg + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long long)gridDim.x * blockDim.x) {
+        double v[3];
+        if (vec4) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pts + i * 4));
+            const double2 b = __ldg(reinterpret_cast<const double2*>(pts + i * 4) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x;
+        } else {
+            const double* q = pts + i * ld;
+            v[0] = __ldg(q); v[1] = __ldg(q + 1); v[2] = __ldg(q + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fmin(mn[k], v[k]);
+            mx[k] = fmax(mx[k], v[k]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        if (lane == 0) {
+            red[k][warp] = mn[k];
+            red[3 + k][warp] = mx[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        double v = red[k][0];
+        for (int w = 1; w < kVoxThreads / 32; ++w) v = k < 3 ? fmin(v, red[k][w]) : fmax(v, red[k][w]);
+        if (k < 3)
+            atomic_min_f64(&mnmx[c * 6 + k], v);
+        else
+            atomic_max_f64(&mnmx[c * 6 + k], v);
+    }
+}
+
+// ------------------------------------------------------------------ step 2: edges
+// pyntcloud VoxelGrid.compute (regular_bounding_box=True) + np.linspace, op by op.
+__global__ void edges_kernel(const double* __restrict__ mnmx, int nx, int ny, int nz, double* __restrict__ edges) {
+    const int c = blockIdx.x;
+    const double* b = mnmx + c * 6;
+    double rng[3], lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) rng[k] = __dsub_rn(b[3 + k], b[k]);  // ptp
+    const double rmax = fmax(rng[0], fmax(rng[1], rng[2]));
+    for (int k = 0; k < 3; ++k) {
+        const double margin = __dsub_rn(rmax, rng[k]);
+        const double half = __ddiv_rn(margin, 2.0);
+        lo[k] = __dsub_rn(b[k], half);
+        hi[k] = __dadd_rn(b[3 + k], half);
+    }
+    const int n[3] = {nx, ny, nz};
+    const int base[3] = {0, nx + 1, nx + 1 + ny + 1};
+    double* e = edges + (size_t)c * (nx + ny + nz + 3);
+    for (int k = 0; k < 3; ++k) {
+        const double delta = __dsub_rn(hi[k], lo[k]);
+        const double step = __ddiv_rn(delta, (double)n[k]);
+        for (int j = threadIdx.x; j <= n[k]; j += blockDim.x) {
+            double v;
+            if (j == n[k])
+                v = hi[k];
+            else if (step == 0.0)
+                v = __dadd_rn(__dmul_rn(__ddiv_rn((double)j, (double)n[k]), delta), lo[k]);
+            else
+                v = __dadd_rn(__dmul_rn((double)j, step), lo[k]);
+            e[base[k] + j] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ step 3: binning
+__global__ void bin_init_kernel(int* __restrict__ count, int* __restrict__ keep_count, long long* __restrict__ maxkey, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        count[i] = 0;
+        if (keep_count) keep_count[i] = 0;
+        if (maxkey) maxkey[i] = (long long)0x8000000000000000ULL;
+    }
+}
+
+// largest j with e[j] < p, or 0 if none; == clip(searchsorted(e, p, 'left') - 1, 0, n-1) for p <= e[n]
+__device__ __forceinline__ int bin_of(const double* __restrict__ e, int n, double p, double lo, double inv_step) {
+    int j = (int)((p - lo) * inv_step);
+    j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+    while (j + 1 <= n - 1 && e[j + 1] < p) ++j;
+    while (j > 0 && !(e[j] < p)) --j;
+    return j;
+}
+
+__global__ void __launch_bounds__(kVoxThreads)
+bin_kernel(const double* __restrict__ pts, int ld, const double* __restrict__ labels, int label_ld,
+           const long long* __restrict__ offsets, const double* __restrict__ edges, int nx, int ny, int nz,
+           const double* __restrict__ keep, int n_keep, int* __restrict__ count, int* __restrict__ keep_count,
+           long long* __restrict__ maxkey, int* __restrict__ lin_out) {
+    extern __shared__ double s_edges[];  // (nx+1)+(ny+1)+(nz+1) doubles, then n_keep keep labels
+    const int c = blockIdx.y;
+    const int ne = nx + ny + nz + 3;
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) s_edges[i] = edges[(size_t)c * ne + i];
+    double* s_keep = s_edges + ne;
+    for (int i = threadIdx.x; i < n_keep; i += blockDim.x) s_keep[i] = keep[i];
+    __syncthreads();
+    const double* ex = s_edges;
+    const double* ey = s_edges + nx + 1;
+    const double* ez = ey + ny + 1;
+    const double lox = ex[0], loy = ey[0], loz = ez[0];
+    const double ivx = (double)nx / (ex[nx] - lox), ivy = (double)ny / (ey[ny] - loy), ivz = (double)nz / (ez[nz] - loz);
+    const long long beg = offsets[c], end = offsets[c + 1];
+    const long long V = (long long)nx * ny * nz;
+    const int lane = threadIdx.x & 31;
+    const bool vec4 = (ld == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
+    const bool lab_in_row = vec4 && labels == pts + 3 && label_ld == 4;
+
+    for (long long base = beg + (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < end;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + lane;
+        const bool valid = i < end;
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        double px, py, pz, lab = 0.0;
+        if (vec4) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pts + i * 4));
+            const double2 b = __ldg(reinterpret_cast<const double2*>(pts + i * 4) + 1);
+            px = a.x; py = a.y; pz = b.x;
+            if (lab_in_row) lab = b.y;
+        } else {
+            const double* q = pts + i * ld;
+            px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+        }
+        if (labels && !lab_in_row) lab = __ldg(labels + i * label_ld);
+        const int vx = bin_of(ex, nx, px, lox, ivx);
+        const int vy = bin_of(ey, ny, py, loy, ivy);
+        const int vz = bin_of(ez, nz, pz, loz, ivz);
+        const int lin = (vz * nx + vx) * ny + vy;  // reference grid layout data[z, x, y]
+        if (lin_out) lin_out[i] = lin;
+        bool is_keep = false;
+        if (labels)
+            for (int k = 0; k < n_keep; ++k) is_keep |= (lab == s_keep[k]);
+        // warp-aggregated atomics: one atomicAdd per distinct voxel per warp
+        const unsigned peers = __match_any_sync(mask, lin);
+        const unsigned kmask = __ballot_sync(mask, is_keep);
+        const bool leader = (__ffs(peers) - 1) == lane;
+        const long long g = (long long)c * V + lin;
+        if (leader) {
+            atomicAdd(&count[g], __popc(peers));
+            const int kc = __popc(peers & kmask);
+            if (keep_count && kc) atomicAdd(&keep_count[g], kc);
+        }
+        if (maxkey && labels) {
+            const long long k = f64_key(lab);
+            if (k > *reinterpret_cast<volatile long long*>(&maxkey[g])) atomicMax(&maxkey[g], k);  // cheap pre-check, most points lose
+        }
+    }
+}
+
+// ------------------------------------------------------------------ step 4: finalize
+__global__ void colminmax_init_kernel(int* __restrict__ cm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cm[i] = (i & 1) ? 0 : 0x7fffffff;  // [.., {min,max}]
+}
+
+// per-(cloud, y) min/max of count over all (z,x) rows; cm [C][ny][2]
+__global__ void __launch_bounds__(kVoxThreads)
+colminmax_kernel(const int* __restrict__ count, int rows, int ny, int rows_per_block, int* __restrict__ cm) {
+    const int c = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    const int* base = count + (size_t)c * rows * ny;
+    // consecutive threads -> consecutive y (coalesced row reads); spare threads take other rows
+    const int ly = ny < (int)blockDim.x ? ny : (int)blockDim.x;
+    const int groups = blockDim.x / ly, grp = threadIdx.x / ly;
+    if (grp >= groups) return;
+    for (int y = threadIdx.x % ly; y < ny; y += ly) {
+        int mn = 0x7fffffff, mx = 0;
+        for (int r = r0 + grp; r < r1; r += groups) {
+            const int v = base[(size_t)r * ny + y];
+            mn = min(mn, v);
+            mx = max(mx, v);
+        }
+        if (mn <= mx) {
+            atomicMin(&cm[((size_t)c * ny + y) * 2], mn);
+            atomicMax(&cm[((size_t)c * ny + y) * 2 + 1], mx);
+        }
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(kVoxThreads)
+finalize_kernel(const int* __restrict__ count, const int* __restrict__ keep_count, const int* __restrict__ cm, long long n,
+                int ny, long long V, double* __restrict__ density, double* __restrict__ frac, double* __restrict__ max_label,
+                TO* __restrict__ occ, TO* __restrict__ occ_keep) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int cnt = count[i];
+        const int kc = keep_count ? keep_count[i] : 0;
+        if (density) {
+            // sklearn MinMaxScaler: scale = 1/range (1 if range == 0); X*scale + (0 - min*scale)
+            const int y = (int)(i % ny);
+            const long long c = i / V;
+            const int mn = cm[(c * ny + y) * 2], mx = cm[(c * ny + y) * 2 + 1];
+            double rng = (double)mx - (double)mn;
+            if (rng == 0.0) rng = 1.0;
+            const double scale = __ddiv_rn(1.0, rng);
+            const double off = __dsub_rn(0.0, __dmul_rn((double)mn, scale));
+            density[i] = __dadd_rn(__dmul_rn((double)cnt, scale), off);
+        }
+        if (frac) frac[i] = cnt > 0 ? __ddiv_rn((double)kc, (double)cnt) : 0.0;
+        if (max_label) {
+            const long long k = reinterpret_cast<const long long*>(max_label)[i];
+            max_label[i] = cnt > 0 ? key_f64(k) : 0.0;
+        }
+        if (occ) occ[i] = cnt > 0 ? (TO)1 : (TO)0;
+        if (occ_keep) occ_keep[i] = kc > 0 ? (TO)1 : (TO)0;
+    }
+}
+
+static inline int blocks_for(long long n, int cap_mult = 8) {
+    long long b = ceil_div64(n, kVoxThreads);
+    const long long cap = (long long)kNumSMs * cap_mult;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace sn
+
+extern "C" int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, double* mnmx, void* stream) {
+    if (!pts || !offsets || !mnmx || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    sn::minmax_init_kernel<<<sn::ceil_div(n_clouds * 6, 128), 128, 0, s>>>(mnmx, n_clouds);
+    SN_LAUNCH_CHECK();
+    // offsets live on the device: size the grid for the machine, blocks grid-stride over their cloud
+    const int bx = max(1, sn::kNumSMs * 4 / n_clouds);
+    sn::minmax_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, 0, s>>>(pts, ld, (const long long*)offsets, mnmx);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int sn_vox_edges(const double* mnmx, int n_clouds, int nx, int ny, int nz, double* edges, void* stream) {
+    if (!mnmx || !edges || n_clouds < 1 || nx < 1 || ny < 1 || nz < 1) return SN_ERR_BAD_ARG;
+    sn::edges_kernel<<<n_clouds, 128, 0, (cudaStream_t)stream>>>(mnmx, nx, ny, nz, edges);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int sn_vox_bin(const double* pts, int ld, const double* labels, int label_ld, const int64_t* offsets,
+                          int n_clouds, int64_t n_points_total, const double* edges, int nx, int ny, int nz,
+                          const double* keep, int n_keep, int32_t* count, int32_t* keep_count, double* max_label,
+                          int32_t* lin_out, void* stream) {
+    if (!pts || !offsets || !edges || !count || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+    if (nx < 1 || ny < 1 || nz < 1 || n_keep < 0 || (n_keep > 0 && !keep) || n_points_total < 0) return SN_ERR_BAD_ARG;
+    if ((long long)nx * ny * nz > 0x7fffffffLL) return SN_ERR_UNSUPPORTED;
+    if (labels && label_ld < 1) return SN_ERR_BAD_ARG;
+    const size_t smem = (size_t)(nx + ny + nz + 3 + n_keep) * sizeof(double);
+    if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nvox = (long long)n_clouds * nx * ny * nz;
+    sn::bin_init_kernel<<<sn::blocks_for(nvox), sn::kVoxThreads, 0, s>>>(count, keep_count, (long long*)max_label, nvox);
+    SN_LAUNCH_CHECK();
+    if (n_points_total == 0) return SN_OK;
+    const long long per_cloud = sn::ceil_div64(n_points_total, n_clouds);
+    int bx = (int)sn::ceil_div64(per_cloud, sn::kVoxThreads);
+    const int cap = max(1, sn::kNumSMs * 8 / n_clouds);
+    bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+    sn::bin_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, smem, s>>>(pts, ld, labels, label_ld, (const long long*)offsets, edges,
+                                                                    nx, ny, nz, keep, n_keep, count, keep_count,
+                                                                    (long long*)max_label, lin_out);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int64_t sn_vox_finalize_workspace_bytes(int n_clouds, int ny) { return (int64_t)n_clouds * ny * 2 * 4; }
+
+extern "C" int sn_vox_finalize(const int32_t* count, const int32_t* keep_count, int n_clouds, int nx, int ny, int nz,
+                               double* density, double* frac, double* max_label, void* occ, void* occ_keep, int out_dtype,
+                               void* ws, void* stream) {
+    if (!count || n_clouds < 1 || nx < 1 || ny < 1 || nz < 1) return SN_ERR_BAD_ARG;
+    if (out_dtype != SN_F32 && out_dtype != SN_F64) return SN_ERR_BAD_ARG;
+    if ((frac || occ_keep) && !keep_count) return SN_ERR_BAD_ARG;
+    if (density && !ws) return SN_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long V = (long long)nx * ny * nz, n = V * n_clouds;
+    int* cm = reinterpret_cast<int*>(ws);
+    if (density) {
+        const int ncm = n_clouds * ny * 2;
+        sn::colminmax_init_kernel<<<sn::ceil_div(ncm, 128), 128, 0, s>>>(cm, ncm);
+        SN_LAUNCH_CHECK();
+        const int rows = nz * nx;
+        const int rpb = max(8, sn::ceil_div(rows, max(1, sn::kNumSMs * 4 / n_clouds)));
+        sn::colminmax_kernel<<<dim3(sn::ceil_div(rows, rpb), n_clouds), sn::kVoxThreads, 0, s>>>(count, rows, ny, rpb, cm);
+        SN_LAUNCH_CHECK();
+    }
+    const int grid = sn::blocks_for(n);
+    if (out_dtype == SN_F32)
+        sn::finalize_kernel<float><<<grid, sn::kVoxThreads, 0, s>>>(count, keep_count, cm, n, ny, V, density, frac, max_label,
+                                                                   (float*)occ, (float*)occ_keep);
+    else
+        sn::finalize_kernel<double><<<grid, sn::kVoxThreads, 0, s>>>(count, keep_count, cm, n, ny, V, density, frac, max_label,
+                                                                    (double*)occ, (double*)occ_keep);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI (include/scenenet_b200.h).
+
+torch is plumbing here: it owns device memory and the stream; all arithmetic happens in the
+hand-written sm_100a kernels of libscenenet_b200.so.  Every function requires CUDA tensors
+and raises otherwise — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import SN_F32, SN_F64, ModelDesc, check, lib
+
+_DT = {torch.float32: SN_F32, torch.float64: SN_F64}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"scenenet_b200: `{name}` must be a CUDA tensor (there is no CPU fallback); got {t.device}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------- model spec
+N_PARAMS = {0: 2, 1: 2, 2: 5, 3: 5, 4: 3, 5: 3}
+
+
+@dataclass
+class ObserverSpec:
+    """Static description of an observer: which operators, in which order, which lambda is last."""
+    kinds: Sequence[int]                 # SN_KIND_* per operator, channel order
+    kernel_size: Sequence[int]           # (kz, kx, ky)
+    lambda_sum_order: Optional[Sequence[int]] = None  # operator ids in lambdas_dict order
+    last_lambda: int = -1                # operator id; -1 = none
+    observer: bool = True                # False: bare kernels (no lambdas)
+
+    def n_param_ptrs(self) -> int:
+        n = sum(N_PARAMS[k] for k in self.kinds)
+        return n + (len(self.kinds) if self.observer else 0)
+
+    def desc(self) -> ModelDesc:
+        G = len(self.kinds)
+        if G < 1 or G > _lib.SN_MAX_GENEOS:
+            raise ValueError(f"between 1 and {_lib.SN_MAX_GENEOS} GENEO operators are supported, got {G}")
+        d = ModelDesc()
+        d.n_geneos = G
+        d.kz, d.kx, d.ky = (int(v) for v in self.kernel_size)
+        off = 0
+        for g, k in enumerate(self.kinds):
+            d.kind[g] = k
+            d.param_index[g] = off
+            off += N_PARAMS[k]
+        for g in range(G):
+            d.lambda_index[g] = off + g if self.observer else -1
+            d.lambda_sum_order[g] = (self.lambda_sum_order[g] if self.lambda_sum_order is not None else g) if self.observer else 0
+        d.n_param_ptrs = off + (G if self.observer else 0)
+        d.last_lambda = self.last_lambda if self.observer else -1
+        return d
+
+    @property
+    def taps(self) -> int:
+        kz, kx, ky = self.kernel_size
+        return int(kz) * int(kx) * int(ky)
+
+
+def _ptr_array(params: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(params))()
+    for i, p in enumerate(params):
+        if p.dtype != torch.float32 or p.numel() != 1:
+            raise TypeError("GENEO parameters must be 0-dim float32 tensors")
+        _need_cuda(p, "parameter")
+        arr[i] = p.data_ptr()
+    return arr
+
+
+def _snapshot_ptr_array(snapshot: torch.Tensor):
+    n = snapshot.numel()
+    arr = (C.c_void_p * n)()
+    base = snapshot.data_ptr()
+    for i in range(n):
+        arr[i] = base + 4 * i
+    return arr
+
+
+# ------------------------------------------------------------------------------- synthesis
+def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lambda: bool = False):
+    """-> (K [G,kz,kx,ky] f32, lambda_eff [G] f32 | None, Kstar [kz,kx,ky] f32 | None, snapshot [n] f32)"""
+    d = spec.desc()
+    if len(params) != d.n_param_ptrs:
+        raise ValueError(f"expected {d.n_param_ptrs} parameter tensors, got {len(params)}")
+    dev = params[0].device
+    G, T = len(spec.kinds), spec.taps
+    K = torch.empty((G, *spec.kernel_size), dtype=torch.float32, device=dev)
+    snap = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=dev)
+    lam = torch.empty(G, dtype=torch.float32, device=dev) if spec.observer else None
+    Kstar = torch.empty(tuple(spec.kernel_size), dtype=torch.float32, device=dev) if spec.observer else None
+    with torch.cuda.device(dev):
+        check(lib.sn_geneo_synth_fwd(C.byref(d), _ptr_array(params), K.data_ptr(), _ptr(lam), _ptr(Kstar),
+                                     snap.data_ptr(), int(write_last_lambda), _stream()), "sn_geneo_synth_fwd")
+    return K, lam, Kstar, snap
+
+
+def synth_bwd(spec: ObserverSpec, snapshot: torch.Tensor, dK: torch.Tensor) -> torch.Tensor:
+    """Jacobian^T dK -> dparams [n_param_ptrs] f32 (evaluated at the snapshot's parameter values)."""
+    d = spec.desc()
+    _need_cuda(dK, "dK")
+    dK = dK.to(torch.float64).contiguous()
+    out = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=dK.device)
+    with torch.cuda.device(dK.device):
+        check(lib.sn_geneo_synth_bwd(C.byref(d), _snapshot_ptr_array(snapshot), dK.data_ptr(), out.data_ptr(), _stream()),
+              "sn_geneo_synth_bwd")
+    return out
+
+
+def param_grads(spec: ObserverSpec, snapshot: torch.Tensor, K: torch.Tensor, lambda_eff: torch.Tensor, W: torch.Tensor,
+                scale: float = 1.0) -> torch.Tensor:
+    d = spec.desc()
+    out = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        check(lib.sn_scenenet_param_grads(C.byref(d), _snapshot_ptr_array(snapshot), K.data_ptr(), lambda_eff.data_ptr(),
+                                          W.data_ptr(), float(scale), out.data_ptr(), _stream()), "sn_scenenet_param_grads")
+    return out
+
+
+# ------------------------------------------------------------------------------- observer
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    """float64 -> float32 with our kernel; float32 passes through (made contiguous)."""
+    _need_cuda(x, "x")
+    if x.dtype == torch.float32:
+        return x.contiguous()
+    if x.dtype != torch.float64:
+        raise TypeError(f"voxel grids must be float32 or float64, got {x.dtype}")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        check(lib.sn_cast_f64_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "sn_cast_f64_to_f32")
+    return out
+
+
+def _grid_dims(x: torch.Tensor):
+    if x.dim() != 5 or x.shape[1] != 1:
+        raise ValueError(f"expected a [B,1,Z,X,Y] voxel grid batch, got {tuple(x.shape)}")
+    B, _, Z, X, Y = x.shape
+    return int(B), int(Z), int(X), int(Y)
+
+
+def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    _need_cuda(x32, "x")
+    B, Z, X, Y = _grid_dims(x32)
+    kz, kx, ky = (int(v) for v in Kstar.shape)
+    pred = torch.empty(x32.shape, dtype=out_dtype, device=x32.device)
+    if x32.numel() == 0:
+        return pred
+    with torch.cuda.device(x32.device):
+        check(lib.sn_scenenet_fwd(x32.data_ptr(), Kstar.data_ptr(), B, Z, X, Y, kz, kx, ky, pred.data_ptr(), _DT[out_dtype],
+                                  _stream()), "sn_scenenet_fwd")
+    return pred
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, kernel_size) -> torch.Tensor:
+    """tap gradient W [kz,kx,ky] float64."""
+    B, Z, X, Y = _grid_dims(x32)
+    kz, kx, ky = (int(v) for v in kernel_size)
+    _need_cuda(dpred, "dpred")
+    if dpred.dtype not in _DT:
+        dpred = dpred.to(torch.float32)
+    dpred = dpred.contiguous()
+    pred = pred.contiguous()
+    W = torch.empty((kz, kx, ky), dtype=torch.float64, device=x32.device)
+    if x32.numel() == 0:
+        return W.zero_()
+    nbytes = int(lib.sn_scenenet_bwd_workspace_bytes(B, Z, X, Y, kz, kx, ky))
+    ws = _workspace(nbytes, x32.device)
+    with torch.cuda.device(x32.device):
+        check(lib.sn_scenenet_bwd(x32.data_ptr(), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
+                                  B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+              "sn_scenenet_bwd")
+    return W
+
+
+def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
+    _need_cuda(p, "p")
+    if p.dtype not in _DT:
+        raise TypeError(f"threshold: float32/float64 only, got {p.dtype}")
+    p = p.contiguous()
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        check(lib.sn_threshold(p.data_ptr(), _DT[p.dtype], float(tau), p.numel(), out.data_ptr(), _stream()), "sn_threshold")
+    return out
+
+
+def fp32_peak_probe(iters: int = 2000, device=None) -> float:
+    """Measured FP32 FMA-pipe peak in TFLOP/s (roofline denominator for the stencils)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    sink = torch.zeros(1, dtype=torch.float32, device=device)
+    flops = C.c_double(0.0)
+    best = 0.0
+    with torch.cuda.device(device):
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.sn_fp32_peak_probe(sink.data_ptr(), iters, C.byref(flops), _stream()), "sn_fp32_peak_probe")
+            e1.record()
+            e1.synchronize()
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,318 @@
+"""GPU parity tests of the model path (synthesis, stencil forward, tap-gradient backward,
+parameter Jacobian) — all through the drop-in modules, i.e. through the C ABI.
+
+Bars (BASELINE.json north_star / SURVEY §8c): kernels <= 1e-6*max|K|; pred allclose(rtol 1e-5,
+atol 1e-6); loss and each of the 11 parameter gradients <= 1e-5 relative — against the REAL
+reference's outputs (tests/golden) and against the CPU oracle on seeded inputs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+RTOL_GRAD = 1e-5
+DEV = "cuda"
+
+
+def _sb():
+    import scenenet_b200 as sb
+    return sb
+
+
+PARAM_SETS = {
+    "kat": dict(radius=2.5, sigma=1.8, apex=4.0, cone_inc=0.3, cone_radius=2.0, neg_factor=0.2),
+    "ckpt": dict(radius=1.5, sigma=0.955910, apex=0.0, cone_inc=0.565547, cone_radius=4.000988, neg_factor=0.127053),
+    "wide": dict(radius=3.0, sigma=0.6, apex=7.0, cone_inc=0.12, cone_radius=1.5, neg_factor=0.9),
+    "apexfull": dict(radius=0.5, sigma=1.0, apex=9.0, cone_inc=0.45, cone_radius=0.5, neg_factor=0.5),
+}
+
+
+def _classes():
+    from scenenet_b200.core.models.geneos import arrow, cylinder, neg_sphere
+    return {"cylinderv2": cylinder.cylinderv2, "cylinder_kernel": cylinder.cylinder_kernel, "arrow": arrow.arrow,
+            "cone_kernel": arrow.cone_kernel, "negSpherev2": neg_sphere.negSpherev2,
+            "neg_sphere_kernel": neg_sphere.neg_sphere_kernel}
+
+
+def test_kernel_synthesis_and_jacobian_vs_reference(golden_dir):
+    ker = np.load(os.path.join(golden_dir, "ref_kernels.npz"))
+    kg = np.load(os.path.join(golden_dir, "ref_kernel_grads.npz"))
+    classes = _classes()
+    n = 0
+    worst_k, worst_g = 0.0, 0.0
+    for key in ker.files:
+        cname, sname, sz = key.split("|")
+        ks = tuple(int(v) for v in sz.split("x"))
+        cls = classes[cname]
+        ps = PARAM_SETS[sname]
+        names = list(cls.abi_params)
+        kw = {k: torch.tensor(float(ps[k]), dtype=torch.float32, device=DEV, requires_grad=(k != "apex")) for k in names}
+        g = cls("g", ks, **kw) if cname == "negSpherev2" else cls("g", ks, False, **kw)
+        K = g.kernel
+        Kref = ker[key]
+        assert tuple(K.shape) == Kref.shape, key
+        scale = max(np.abs(Kref).max(), 1e-30)
+        err = np.abs(K.detach().cpu().numpy() - Kref).max() / scale
+        worst_k = max(worst_k, err)
+        assert err <= 1e-6, (key, err)
+        R = np.random.default_rng(int(kg[key + "|seed"])).standard_normal(Kref.shape)
+        (K.to(torch.float64) * torch.from_numpy(R).to(DEV)).sum().backward()
+        got = np.array([0.0 if (k == "apex" or kw[k].grad is None) else float(kw[k].grad) for k in sorted(names)])
+        ref = kg[key + "|g"]
+        tol = RTOL_GRAD * np.abs(ref) + 1e-6 * np.abs(ref).max() + 1e-12
+        assert np.all(np.abs(got - ref) <= tol), (key, got, ref)
+        worst_g = max(worst_g, float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-30) * (np.abs(ref) > 1e-3 * np.abs(ref).max()))))
+        n += 1
+    assert n > 150
+    print(f"kernels checked: {n}; worst |dK|/max|K| = {worst_k:.2e}; worst significant grad rel err = {worst_g:.2e}")
+
+
+def _make_model(params, lambdas, last, ks, v1=False, geneo_num=None):
+    sb = _sb()
+    torch.manual_seed(0)
+    cls = sb.SCENE_Net if v1 else sb.SceneNet
+    m = cls(dict(geneo_num or mo.KAT_GENEO_NUM), tuple(ks)) if not v1 else cls(dict(geneo_num or mo.KAT_GENEO_NUM), tuple(ks), False, torch.device(DEV))
+    m = m.to(DEV)
+    with torch.no_grad():
+        for name, layer in m.geneos.items():
+            for pn, p in layer.geneo_params.items():
+                p.fill_(float(params[f"{name}.{pn}"]))
+        for ln, p in m.lambdas_dict.items():
+            p.fill_(float(lambdas[ln]))
+            p.requires_grad_(ln != last)
+    m.last_lambda = last
+    return m
+
+
+def _criterion(pred, y, m):
+    return mo.geneo_tversky_criterion(pred, y, m.get_cvx_coefficients(), m.last_lambda, list(m.get_geneo_params().values()))
+
+
+def _grads(m):
+    return {n: (None if p.grad is None else float(p.grad)) for n, p in m.named_parameters()}
+
+
+def _check_grads(got, names, ref_vals, rtol=RTOL_GRAD):
+    worst = 0.0
+    for name, r in zip(names, ref_vals):
+        g = got[str(name)]
+        if np.isnan(r):
+            assert g is None, name
+        else:
+            assert g is not None, name
+            rel = abs(g - r) / max(abs(r), 1e-30)
+            worst = max(worst, rel)
+            assert rel <= rtol or abs(g - r) <= 1e-12, (str(name), g, r, rel)
+    return worst
+
+
+def _x575(golden_dir):
+    v = np.load(os.path.join(golden_dir, "vox_sample_575.npz"))
+    x = np.zeros(64 ** 3)
+    x[v["restated_density_idx"]] = 1.0
+    y = np.zeros(64 ** 3)
+    y[v["ref_frac_idx"]] = 1.0
+    return (torch.from_numpy(x).view(1, 1, 64, 64, 64).to(DEV), torch.from_numpy(y).view(1, 1, 64, 64, 64).to(DEV))
+
+
+@pytest.mark.parametrize("tag,v1", [("kat575", False), ("ckpt575", False), ("v1_575", True)])
+def test_config1_against_reference_outputs(golden_dir, tag, v1):
+    gold = np.load(os.path.join(golden_dir, "ref_model.npz"))
+    if tag == "ckpt575":
+        cfg = json.loads(str(gold["ckpt|params"]))
+        params, lambdas, last = cfg["params"], cfg["lambdas"], cfg["last"]
+    else:
+        params, lambdas = mo.KAT_PARAMS, mo.KAT_LAMBDAS
+        last = "lambda_cone_0" if v1 else mo.KAT_LAST
+    x, y = _x575(golden_dir)
+    m = _make_model(params, lambdas, last, (9, 5, 5), v1=v1)
+    pred = m(x)
+    assert pred.dtype == torch.float64 and pred.shape == x.shape
+    loss = _criterion(pred, y, m)
+    loss.backward()
+    p = pred.detach().cpu().numpy().reshape(-1)
+    ref = np.zeros_like(p)
+    ref[gold[f"{tag}|pred_idx"]] = gold[f"{tag}|pred_val"]
+    assert np.allclose(p, ref, rtol=1e-5, atol=1e-6), np.abs(p - ref).max()
+    assert int((p > 0).sum()) == int(gold[f"{tag}|pred_nnz"])
+    assert abs(int((p >= 0.65).sum()) - int(gold[f"{tag}|pred_ge065"])) <= 1
+    assert abs(p.sum() - float(gold[f"{tag}|pred_sum"])) <= 1e-5 * abs(p.sum())
+    rl = float(gold[f"{tag}|loss"])
+    assert abs(float(loss) - rl) <= 1e-5 * abs(rl), (float(loss), rl)
+    worst = _check_grads(_grads(m), gold[f"{tag}|grads_names"], gold[f"{tag}|grads"])
+    # kernels inside the model equal the reference's
+    K = torch.stack([m.geneos[g].compute_kernel() for g in m.geneos]).detach().cpu().numpy()
+    Kref = gold[f"{tag}|kernels"]
+    assert np.abs(K - Kref).max() <= 1e-6 * np.abs(Kref).max()
+    print(f"{tag}: loss rel err {abs(float(loss) - rl) / abs(rl):.2e}, worst grad rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("ks", [(9, 7, 7), (6, 5, 5), (9, 6, 6), (7, 7, 7)])
+def test_synthetic_fixed_upstream_gradient(golden_dir, ks):
+    gold = np.load(os.path.join(golden_dir, "ref_model.npz"))
+    tag = f"syn32_{ks[0]}x{ks[1]}x{ks[2]}"
+    x, _ = mo.synthetic_grids(2, (32, 32, 32), seed=1234)
+    dpred = torch.randn(x.shape, generator=torch.Generator().manual_seed(1235), dtype=torch.float64)
+    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, "lambda_neg_0", ks)
+    pred = m(x.to(DEV))
+    pred.backward(dpred.to(DEV))
+    p = pred.detach().cpu().numpy().reshape(-1)
+    ref = np.zeros_like(p)
+    ref[gold[f"{tag}|pred_idx"]] = gold[f"{tag}|pred_val"]
+    assert np.allclose(p, ref, rtol=1e-5, atol=1e-6), np.abs(p - ref).max()
+    worst = _check_grads(_grads(m), gold[f"{tag}|grads_names"], gold[f"{tag}|grads"])
+    print(f"{tag}: worst grad rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("tag", ["syn64_crit", "syn64_dpred"])
+def test_config2_shape_b2(golden_dir, tag):
+    gold = np.load(os.path.join(golden_dir, "ref_model.npz"))
+    x, y = mo.synthetic_grids(2, (64, 64, 64), seed=1234)
+    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+    pred = m(x.to(DEV))
+    if tag == "syn64_crit":
+        loss = _criterion(pred, y.to(DEV), m)
+        loss.backward()
+        rl = float(gold[f"{tag}|loss"])
+        assert abs(float(loss) - rl) <= 1e-5 * abs(rl)
+    else:
+        dpred = torch.randn(x.shape, generator=torch.Generator().manual_seed(1235), dtype=torch.float64)
+        pred.backward(dpred.to(DEV))
+    ps = float(pred.sum())
+    assert abs(ps - float(gold[f"{tag}|pred_sum"])) <= 1e-5 * abs(ps)
+    assert int((pred > 0).sum()) == int(gold[f"{tag}|pred_nnz"])
+    worst = _check_grads(_grads(m), gold[f"{tag}|grads_names"], gold[f"{tag}|grads"])
+    print(f"{tag}: worst grad rel err {worst:.2e}")
+
+
+def _oracle_case(geneo_num, ks, grid, B, seed, last=None, dense=False, dtype=torch.float64):
+    """random parameters through the CUDA model and the CPU oracle on the same inputs"""
+    sb = _sb()
+    torch.manual_seed(seed)
+    m = sb.SceneNet(dict(geneo_num), tuple(ks)).to(DEV)
+    with torch.no_grad():  # keep apex inside the kernel
+        for layer in m.geneos.values():
+            if "apex" in layer.geneo_params:
+                layer.geneo_params["apex"].fill_(float(min(int(layer.geneo_params["apex"]), ks[0])))
+    params = {f"{n}.{pn}": float(p) for n, l in m.geneos.items() for pn, p in l.geneo_params.items()}
+    lambdas = {k: float(v) for k, v in m.lambdas_dict.items()}
+    o = mo.OracleSceneNet(dict(geneo_num), ks, params, lambdas, m.last_lambda)
+    g = torch.Generator().manual_seed(seed + 100)
+    if dense:
+        x = torch.rand((B, 1, *grid), generator=g, dtype=torch.float64)
+    else:
+        x = (torch.rand((B, 1, *grid), generator=g) < 0.05).to(torch.float64)
+    dpred = torch.randn(x.shape, generator=g, dtype=torch.float64)
+    pr, _, gr = mo.fwd_bwd(o, x, None, dpred)
+    pred = m(x.to(DEV, dtype))
+    assert pred.dtype == dtype
+    pred.backward(dpred.to(DEV, dtype))
+    assert torch.allclose(pred.detach().cpu().to(torch.float64), pr, rtol=1e-5, atol=2e-6), (pred.detach().cpu() - pr).abs().max()
+    got = _grads(m)
+    worst = 0.0
+    gmax = max(abs(v) for v in gr.values() if v is not None)
+    for n, r in gr.items():
+        if r is None:
+            assert got[n] is None, n
+            continue
+        rel = abs(got[n] - r) / max(abs(r), 1e-30)
+        # the reference's own float32 autograd noise floor: tiny gradients are compared absolutely
+        assert rel <= RTOL_GRAD or abs(got[n] - r) <= 2e-6 * gmax, (n, got[n], r, rel)
+        worst = max(worst, rel if abs(r) > 1e-3 * gmax else 0.0)
+    return worst
+
+
+@pytest.mark.parametrize("geneo_num,ks,grid,B", [
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), (20, 17, 23), 2),      # ragged grid (Y % 4 != 0 -> plain loads)
+    ({'cy': 2, 'cone': 1, 'neg': 2}, (9, 7, 7), (24, 24, 24), 1),      # 5 operators
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (3, 3, 3), (16, 16, 16), 3),
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (5, 5, 4), (12, 12, 12), 1),      # ky=4 -> generic fallback kernels
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (11, 11, 11), (32, 32, 32), 1),   # config-4 style cubic kernels
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (9, 9, 9), (32, 32, 32), 1),
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (13, 13, 13), (24, 24, 24), 1),
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (15, 15, 15), (24, 24, 64), 1),
+    ({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), (8, 8, 128), 2),       # several y tiles
+    ({'cy': 1, 'cone': 0, 'neg': 1}, (4, 6, 5), (16, 16, 16), 2),      # even extents, no cone
+])
+def test_cuda_vs_oracle_random_params(geneo_num, ks, grid, B):
+    worst = _oracle_case(geneo_num, ks, grid, B, seed=11)
+    print(f"{geneo_num} {ks} {grid}: worst significant grad rel err {worst:.2e}")
+
+
+def test_dense_float_input_and_f32_dtype():
+    """non-binary density grids (ToFullDense off) and float32 callers"""
+    w1 = _oracle_case({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), (32, 32, 32), 2, seed=5, dense=True)
+    w2 = _oracle_case({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), (32, 32, 32), 2, seed=6, dtype=torch.float32)
+    print(f"dense x: {w1:.2e}; float32 io: {w2:.2e}")
+
+
+def test_last_lambda_side_effect_and_frozen_params():
+    m = _make_model(mo.KAT_PARAMS, {"lambda_cone_0": 0.3, "lambda_cy_0": 9.0, "lambda_neg_0": 0.25}, "lambda_cy_0", (9, 5, 5))
+    x, _ = mo.synthetic_grids(1, (16, 16, 16))
+    p = m(x.to(DEV))
+    # SCENE_Net.py:333: the last lambda is replaced by 1 - sum(all) + itself, evaluated in float32
+    lam = torch.tensor([0.3, 9.0, 0.25], dtype=torch.float32)
+    expect = (1 - ((0 + lam[0]) + lam[1] + lam[2])) + lam[1]
+    assert float(m.lambdas_dict["lambda_cy_0"]) == float(expect)
+    assert not m.lambdas_dict["lambda_cy_0"].requires_grad
+    p.sum().backward()
+    assert m.lambdas_dict["lambda_cy_0"].grad is None
+    assert m.geneos["cone_0"].geneo_params["apex"].grad is None
+    assert m.lambdas_dict["lambda_neg_0"].grad is not None
+
+
+def test_properties_at_config2_full_size():
+    """B=32, 64^3 (BASELINE config 2): size-independent properties instead of a CPU comparison."""
+    x, _ = mo.synthetic_grids(32, (64, 64, 64), seed=1234, dtype=torch.float32)
+    x = x.to(DEV)
+    g = torch.Generator().manual_seed(1235)
+    d1 = torch.randn(x.shape, generator=g).to(DEV)
+    d2 = torch.randn(x.shape, generator=g).to(DEV)
+
+    def run(dp, xin=x):
+        m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+        pred = m(xin)
+        pred.backward(dp)
+        return pred.detach(), torch.tensor([0.0 if p.grad is None else float(p.grad) for p in m.parameters()], dtype=torch.float64)
+
+    p1, g1 = run(d1)
+    p1b, g1b = run(d1)
+    assert torch.equal(p1, p1b) and torch.equal(g1, g1b), "forward/backward must be deterministic"
+    assert float(p1.min()) >= 0.0 and float(p1.max()) < 1.0
+    _, g2 = run(d2)
+    _, g12 = run(2.0 * d1 + d2)
+    assert torch.allclose(g12, 2.0 * g1 + g2, rtol=1e-4, atol=1e-4 * float(g12.abs().max())), "backward is linear in dpred"
+    # translation equivariance away from the borders: shifting the input shifts the prediction
+    xs = torch.roll(x, shifts=(8, 8, 8), dims=(2, 3, 4))
+    ps, _ = run(d1, xs)
+    assert torch.equal(torch.roll(p1, shifts=(8, 8, 8), dims=(2, 3, 4))[:, :, 16:48, 16:48, 16:48], ps[:, :, 16:48, 16:48, 16:48])
+    # empty input -> zero prediction and zero gradients
+    pz, gz = run(d1, torch.zeros_like(x))
+    assert float(pz.abs().max()) == 0.0 and float(gz.abs().max()) == 0.0
+
+
+def test_threshold_and_classifier():
+    sb = _sb()
+    from scenenet_b200.utils import voxelization as Vox
+    p = torch.rand(2, 1, 16, 16, 16, dtype=torch.float64, device=DEV)
+    p[0, 0, 0, 0, 0] = 0.65
+    t = Vox.prob_to_label(p, 0.65)
+    assert t.dtype == p.dtype and torch.equal(t, (p >= 0.65).to(p.dtype))
+    a = np.random.default_rng(0).random((8, 8, 8)).astype(np.float32)
+    assert np.array_equal(Vox.prob_to_label(a, 0.5), (a >= 0.5).astype(a.dtype))
+
+
+def test_empty_batch_and_errors():
+    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+    out = m(torch.zeros(0, 1, 8, 8, 8, dtype=torch.float64, device=DEV))
+    assert out.shape == (0, 1, 8, 8, 8)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 2, 8, 8, 8, dtype=torch.float64, device=DEV))
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 1, 8, 8, 8, dtype=torch.int32, device=DEV))
