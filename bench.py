@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — SCENE-Net hot-path benchmark (BASELINE.json metric: voxel grids/s, 64^3 GENEO fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch: SceneNet forward (kernel synthesis + cast +
+stencil/observer) and backward (tap-gradient reduction + parameter Jacobian) on a batch of 32
+synthetic TS40K-shaped 64^3 occupancy grids per GPU (BASELINE config 2), driven by a
+fixed upstream gradient dL/dpred ~ N(0,1).  Rank r owns its own batches (weak scaling); with
+N > 1 the 13-float parameter-gradient payload is all-reduced (mean) over NCCL every step.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU = 32
+GRID = (64, 64, 64)
+KERNEL = (9, 5, 5)
+P_OCC = 0.016
+METRIC = "voxel grids/s (64^3 GENEO fwd+bwd)"
+UNIT = "grids/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ----------------------------------------------------------------------------------------------
+def kat_model(device):
+    """SceneNet({'cy':1,'cone':1,'neg':1}, (9,5,5)) with the SURVEY §8c parameter vector."""
+    import scenenet_b200 as sb
+    params = {"cy_0.radius": 2.5, "cy_0.sigma": 1.8, "cone_0.apex": 4.0, "cone_0.cone_inc": 0.3, "cone_0.cone_radius": 2.0,
+              "cone_0.radius": 3.0, "cone_0.sigma": 1.4, "neg_0.neg_factor": 0.2, "neg_0.radius": 8.0, "neg_0.sigma": 0.8}
+    lambdas = {"lambda_cone_0": 0.3, "lambda_cy_0": 0.45, "lambda_neg_0": 0.25}
+    torch.manual_seed(0)
+    m = sb.SceneNet({'cy': 1, 'cone': 1, 'neg': 1}, KERNEL).to(device)
+    with torch.no_grad():
+        for name, layer in m.geneos.items():
+            for pn, p in layer.geneo_params.items():
+                p.fill_(params[f"{name}.{pn}"])
+        for ln, p in m.lambdas_dict.items():
+            p.fill_(lambdas[ln])
+            p.requires_grad_(ln != "lambda_cy_0")
+    m.last_lambda = "lambda_cy_0"
+    return m
+
+
+def make_pool(device, rank, n_sets, dtype):
+    """n_sets distinct (x, dpred) batches so that consecutive steps never find their inputs in L2."""
+    pool = []
+    for s in range(n_sets):
+        g = torch.Generator(device=device).manual_seed(1234 + 1000 * rank + s)
+        x = (torch.rand((B_PER_GPU, 1, *GRID), generator=g, device=device) < P_OCC).to(dtype)
+        dp = torch.randn((B_PER_GPU, 1, *GRID), generator=g, device=device, dtype=torch.float32).to(dtype)
+        pool.append((x, dp))
+    return pool
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": (max(mx) if mx else None), "reasons": reasons,
+                "samples": len(sm), "power_w_max": (max(pw) if pw else None)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- CPU arms
+def cpu_step_fn(batch):
+    """The oracle port of the reference's CPU path: float64 conv3d + autograd, all host threads."""
+    from oracle import model_oracle as mo
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = mo.kat_model(KERNEL)
+    x, _ = mo.synthetic_grids(batch, GRID, seed=1234)
+    dpred = torch.randn(x.shape, generator=torch.Generator().manual_seed(1235), dtype=torch.float64)
+
+    def step():
+        mo.fwd_bwd(model, x, None, dpred)
+    return step
+
+
+def time_cpu(batch, steps, warmup):
+    step = cpu_step_fn(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    v, per_step = time_cpu(batch, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "SCENE-Net training step fwd+bwd, synthetic TS40K-shaped 64^3 grids, kernel (9,5,5), G=3 "
+                               f"(BASELINE config 2); CPU step = bounded sample of {batch} grids of the 32-grid batch"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{batch} of 32 grids per step, oracle port of the reference's float64 PyTorch CPU path "
+                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--io-dtype", default="f64", choices=["f64", "f32"], help="dtype of x / dpred / pred at the module boundary")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import scenenet_b200 as sb
+    from scenenet_b200 import dist as sdist, ops
+    import torch.distributed as dist
+
+    rank, world, device = sdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scenenet_b200 hot path has no CPU fallback")
+    io_dtype = torch.float64 if args.io_dtype == "f64" else torch.float32
+    model = kat_model(device)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    model.grad_scale = 1.0 / world  # DDP mean folded into the backward kernel; the collective only sums
+
+    bytes_per_set = B_PER_GPU * GRID[0] * GRID[1] * GRID[2] * (8 if io_dtype == torch.float64 else 4) * 3
+    n_sets = max(3, -(-4 * L2_BYTES // bytes_per_set))
+    pool = make_pool(device, rank, n_sets, io_dtype)
+
+    def step(i):
+        x, dp = pool[i % n_sets]
+        for p in trainable:
+            p.grad = None
+        pred = model(x)
+        pred.backward(dp)
+        if world > 1:
+            sdist.allreduce_mean_grads(trainable, already_scaled=True)
+        return pred
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    barrier()
+
+    sampler = ClockSampler(device.index or 0)
+    if rank == 0:
+        sampler.start()
+    n0 = sb._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = sb._lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    value = B_PER_GPU * world * args.steps / (total_ms * 1e-3)
+
+    # ------------------------------------------------ e2e: host buffers, copies inside the timed region
+    xh = [torch.empty(pool[0][0].shape, dtype=io_dtype).pin_memory() for _ in range(2)]
+    for h in xh:
+        h.copy_(pool[0][0])
+    xd = torch.empty_like(pool[0][0])
+    n_e2e = max(3, min(args.steps, 20))
+
+    def e2e_step(i):
+        xd.copy_(xh[i % 2], non_blocking=True)               # H2D of this step's input grids
+        for p in trainable:
+            p.grad = None
+        pred = model(xd)
+        pred.backward(pool[i % n_sets][1])
+        if world > 1:
+            sdist.allreduce_mean_grads(trainable, already_scaled=True)
+        return torch.stack([p.grad for p in trainable]).cpu()  # D2H read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        g_host = e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = B_PER_GPU * world * n_e2e / float(e2e_s)
+    h2d = xd.numel() * xd.element_size()
+    d2h = g_host.numel() * g_host.element_size()
+
+    # ------------------------------------------------ roofline of the two stencil kernels, timed alone with CUDA events
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        T = KERNEL[0] * KERNEL[1] * KERNEL[2]
+        V = B_PER_GPU * GRID[0] * GRID[1] * GRID[2]
+        peak_tf = ops.fp32_peak_probe(2000, device)
+        hbm_gbs, hbm_src = measured_peaks()
+        x32s = [ops.cast_f32(p[0]) for p in pool]
+        K, lam, Kstar, snap = ops.synth_fwd(*_spec_params(model))
+        preds = [ops.scenenet_fwd(x32, Kstar, io_dtype) for x32 in x32s]
+        reps = 20
+
+        def time_kernel(fn):
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(i)
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b) / reps * 1e-3
+
+        t_fwd = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype))
+        t_bwd = time_kernel(lambda i: ops.scenenet_bwd(x32s[i % n_sets], preds[i % n_sets], pool[i % n_sets][1], KERNEL))
+        fl = 2.0 * T * V
+        esz = 8 if io_dtype == torch.float64 else 4
+        dom, t_dom, bytes_dom = ("stencil_bwd_kernel", t_bwd, V * (4 + 2 * esz)) if t_bwd >= t_fwd else ("stencil_fwd_kernel", t_fwd, V * (4 + esz))
+        roof = {
+            "bound": "fp32", "kernel": dom, "achieved": fl / t_dom / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": fl / t_dom / 1e12 / peak_tf, "traffic": None,
+            "peak_source": "FP32 FFMA probe measured in this run (sn_fp32_peak_probe); MEASURED_PEAKS.json has no FP32-pipe figure",
+            "algorithmic": {"flops_per_voxel_per_kernel": 2 * T, "voxels_per_launch": V, "bytes_per_launch": bytes_dom},
+            "hbm": {"achieved": bytes_dom / t_dom / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": bytes_dom / t_dom / 1e9 / hbm_gbs,
+                    "peak_source": hbm_src},
+            "fwd": {"us": t_fwd * 1e6, "tflops": fl / t_fwd / 1e12, "frac": fl / t_fwd / 1e12 / peak_tf},
+            "bwd": {"us": t_bwd * 1e6, "tflops": fl / t_bwd / 1e12, "frac": fl / t_bwd / 1e12 / peak_tf},
+            "step_roofline_grids_per_s": B_PER_GPU / (2 * fl / (peak_tf * 1e12)),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, per = time_cpu(2, 3, 1)
+            cpu_base = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "2 of the 32 grids, 1 warm-up + 3 timed fwd+bwd steps of the oracle port (float64 conv3d + autograd)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SCENE-Net training step fwd+bwd (13 params, 11 trainable), batch 32 per GPU of synthetic "
+                                   "TS40K-shaped 64^3 occupancy grids (Bernoulli 0.016), kernel (9,5,5), G=3, fixed upstream "
+                                   "dL/dpred ~ N(0,1) (BASELINE config 2)",
+                       "global_batch": B_PER_GPU * world, "io_dtype": args.io_dtype, "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                    "note": "x from pinned host memory each step; dL/dpred resident on the device (config 2(i)); gradients read back"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _spec_params(model):
+    spec, params = model._spec_and_params()
+    return spec, [p.detach() for p in params]
+
+
+if __name__ == "__main__":
+    main()

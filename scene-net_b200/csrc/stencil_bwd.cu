@@ -46,7 +46,7 @@ __device__ __forceinline__ void bwd_chunk(float (&acc)[Geo<KY>::C * KY], const f
                 for (int dy = 0; dy < KY; ++dy) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        acc[dzl * KY + dy] = fmaf(g[zo][r], win[r + dy], acc[dzl * KY + dy]);
+                        acc[dzl * KY + dy] = fmaf(g[zo][r], win[Geo<KY>::OFF + r + dy], acc[dzl * KY + dy]);
                 }
             }
         }

@@ -19,11 +19,18 @@ __host__ __device__ constexpr int cmax_for(int ky) {
 }
 __host__ __device__ constexpr int round4(int v) { return (v + 3) & ~3; }
 
+// TMA constraint measured on B200 (scratch experiments): with SWIZZLE_NONE the innermost
+// start coordinate of a tiled load must be a multiple of 16 bytes (c0 = -2 floats raises an
+// illegal-instruction fault, c0 = -4 is fine).  The halo box therefore starts PLA = round4(pad_left)
+// columns left of the tile and the first OFF = PLA - pad_left floats of every window are dead.
 template <int KY>
 struct Geo {
     static constexpr int C = cmax_for(KY);
     static constexpr int CKP = round4(C * KY);  // taps of one (dx, chunk) slot, padded for 16-byte loads
-    static constexpr int WN = round4(KY + 3);   // window floats a thread reads per input row
+    static constexpr int PL = (KY - 1) / 2;     // 'same' left pad along y
+    static constexpr int PLA = round4(PL);      // left extent of the halo box (16-byte aligned start)
+    static constexpr int OFF = PLA - PL;        // dead floats at the start of a thread's window
+    static constexpr int WN = round4(OFF + KY + 3);  // window floats a thread reads per input row
 };
 
 struct FwdParams {
@@ -52,7 +59,7 @@ struct TileGeo {
     int HZ, HX, WS;      // halo tile extents (rows, rows, padded row length in floats)
     int tiles_z, tiles_x, tiles_y, ntiles;
     int nchunks;         // ceil(kz / C)
-    int plz, plx, ply;   // left pads
+    int plz, plx, ply;   // left extents of the halo box (ply is rounded up to 4 floats, see Geo)
 };
 
 template <int KY, int TYT>
@@ -62,7 +69,7 @@ __host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, 
     g.TX = kStencilThreads / TYT;
     g.HZ = kRZ + kz - 1;
     g.HX = g.TX + kx - 1;
-    g.WS = round4(g.TY + KY - 1);
+    g.WS = round4(g.TY + Geo<KY>::OFF + KY - 1);
     g.tiles_z = ceil_div(Z, kRZ);
     g.tiles_x = ceil_div(X, g.TX);
     g.tiles_y = ceil_div(Y, g.TY);
@@ -70,7 +77,7 @@ __host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, 
     g.nchunks = ceil_div(kz, Geo<KY>::C);
     g.plz = pad_left(kz);
     g.plx = pad_left(kx);
-    g.ply = pad_left(KY);
+    g.ply = Geo<KY>::PLA;  // box start (aligned), not the conv pad
     return g;
 }
 

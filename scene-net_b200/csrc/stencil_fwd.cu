@@ -38,7 +38,7 @@ __device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __r
 #pragma unroll
                 for (int dy = 0; dy < KY; ++dy) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[zo][r] = fmaf(win[r + dy], tap[dzl * KY + dy], acc[zo][r]);
+                    for (int r = 0; r < 4; ++r) acc[zo][r] = fmaf(win[Geo<KY>::OFF + r + dy], tap[dzl * KY + dy], acc[zo][r]);
                 }
             }
         }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace sn {
@@ -28,6 +29,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 // cannot express the tensor (caller falls back to plain loads).
 inline bool make_grid_tmap(CUtensorMap* m, const float* x, int B, int Z, int X, int Y, int boxZ, int boxX, int boxY) {
     memset(m, 0, sizeof(*m));
+    static const bool disabled = getenv("SN_NO_TMA") != nullptr;  // debugging aid: force the plain-load path
+    if (disabled) return false;
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     if ((Y & 3) || ((uintptr_t)x & 15)) return false;               // global strides must be multiples of 16 B
