@@ -41,8 +41,21 @@ class _ObserverFunction(torch.autograd.Function):
         x32, pred, K, lam, snap = ctx.saved_tensors
         W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size)
         d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
-        grads = [d[i] if ctx.needs_input_grad[i + 4] else None for i in range(d.numel())]
+        unused = ctx.spec.unused
+        grads = [d[i] if (ctx.needs_input_grad[i + 4] and i not in unused) else None for i in range(d.numel())]
         return (None, None, None, None, *grads)
+
+
+def _apex_int(layer) -> int:
+    """int(apex) of a cone/arrow layer.  The reference reads it with .item() on every forward (a
+    device sync, arrow.py:235); apex is frozen, so the host value is cached until the tensor changes."""
+    p = layer.geneo_params['apex']
+    key = (p.data_ptr(), p._version)
+    cached = getattr(layer, '_apex_cache', None)
+    if cached is None or cached[0] != key:
+        cached = (key, int(p.detach().to(torch.int).item()))
+        layer._apex_cache = cached
+    return cached[1]
 
 
 ###############################################################
@@ -167,13 +180,21 @@ class _SceneNetBase(nn.Module):
             raise ValueError(f"all GENEO kernels of an observer must share one kernel_size, got {ks}")
         kinds = [KIND[l.geneo_class.kind_name] for l in layers]
         params = []
-        for l in layers:
+        unused = set()
+        kz = next(iter(ks))[0]
+        for l, kind in zip(layers, kinds):
+            if kind in (KIND["cone_kernel"], KIND["arrow"]):
+                hc = _apex_int(l)
+                if hc < 0 or hc > kz:
+                    raise ValueError(f"int(apex) = {hc} must lie in [0, kernel_size[0] = {kz}] ({l.name})")
+                unused |= ops.unused_cone_params(kind, hc, kz, len(params))
             params.extend(l.geneo_params[p] for p in l.geneo_class.abi_params)
         lam_keys = list(self.lambdas_dict.keys())  # iteration order of sum(self.lambdas_dict.values())
         order = [names.index(k[len('lambda_'):]) for k in lam_keys]
         params.extend(self.lambdas_dict[f'lambda_{n}'] for n in names)
         spec = ops.ObserverSpec(kinds=kinds, kernel_size=ks.pop(), lambda_sum_order=order,
-                                last_lambda=names.index(self.last_lambda[len('lambda_'):]), observer=True)
+                                last_lambda=names.index(self.last_lambda[len('lambda_'):]), observer=True,
+                                unused=frozenset(unused))
         return spec, params
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -28,7 +28,8 @@ class _KernelSynthesis(torch.autograd.Function):
     def backward(ctx, dK):
         (snap,) = ctx.saved_tensors
         d = ops.synth_bwd(ctx.spec, snap, dK.reshape(1, -1))
-        return (None, *[d[i] if ctx.needs_input_grad[i + 1] else None for i in range(d.numel())])
+        return (None, *[d[i] if (ctx.needs_input_grad[i + 1] and i not in ctx.spec.unused) else None
+                        for i in range(d.numel())])
 
 
 def _as_param(v, device):
@@ -68,8 +69,12 @@ class GENEO_kernel_torch:
 
     def compute_kernel(self) -> torch.Tensor:
         """Returns the 3-D GENEO kernel [kz,kx,ky], float32, differentiable."""
-        spec = ops.ObserverSpec(kinds=[KIND[self.kind_name]], kernel_size=tuple(int(k) for k in self.kernel_size),
-                                observer=False)
+        kind = KIND[self.kind_name]
+        unused = frozenset()
+        if hasattr(self, "apex"):
+            unused = frozenset(ops.unused_cone_params(kind, int(float(self.apex)), int(self.kernel_size[0]), 0))
+        spec = ops.ObserverSpec(kinds=[kind], kernel_size=tuple(int(k) for k in self.kernel_size), observer=False,
+                                unused=unused)
         params = [_as_param(v, self.device) for v in self._abi_values()]
         return _KernelSynthesis.apply(spec, *params)
 

@@ -120,12 +120,12 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gz < p.Z && gx < p.X && gy < p.Y) {
                 const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
-                float pv[4], dv[4];
+                double pv[4], dv[4];
                 if (vec) {
                     if (p.pred_f64) {
                         const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[0];
                         const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[1];
-                        pv[0] = (float)a.x; pv[1] = (float)a.y; pv[2] = (float)c.x; pv[3] = (float)c.y;
+                        pv[0] = a.x; pv[1] = a.y; pv[2] = c.x; pv[3] = c.y;
                     } else {
                         const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pred) + idx);
                         pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
@@ -133,7 +133,7 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
                     if (p.dpred_f64) {
                         const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[0];
                         const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[1];
-                        dv[0] = (float)a.x; dv[1] = (float)a.y; dv[2] = (float)c.x; dv[3] = (float)c.y;
+                        dv[0] = a.x; dv[1] = a.y; dv[2] = c.x; dv[3] = c.y;
                     } else {
                         const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dpred) + idx);
                         dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w;
@@ -142,12 +142,12 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const bool ok = gy + r < p.Y;
-                        pv[r] = !ok ? 0.f
-                                    : (p.pred_f64 ? (float)reinterpret_cast<const double*>(p.pred)[idx + r]
-                                                  : reinterpret_cast<const float*>(p.pred)[idx + r]);
-                        dv[r] = !ok ? 0.f
-                                    : (p.dpred_f64 ? (float)reinterpret_cast<const double*>(p.dpred)[idx + r]
-                                                   : reinterpret_cast<const float*>(p.dpred)[idx + r]);
+                        pv[r] = !ok ? 0.0
+                                    : (p.pred_f64 ? reinterpret_cast<const double*>(p.pred)[idx + r]
+                                                  : (double)reinterpret_cast<const float*>(p.pred)[idx + r]);
+                        dv[r] = !ok ? 0.0
+                                    : (p.dpred_f64 ? reinterpret_cast<const double*>(p.dpred)[idx + r]
+                                                   : (double)reinterpret_cast<const float*>(p.dpred)[idx + r]);
                     }
                 }
                 o = make_float4(g0_of(pv[0], dv[0]), g0_of(pv[1], dv[1]), g0_of(pv[2], dv[2]), g0_of(pv[3], dv[3]));

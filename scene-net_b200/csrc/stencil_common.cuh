@@ -51,7 +51,10 @@ struct BwdParams {
     int ncombos, combos_per_cta, TP;
 };
 
-__device__ __forceinline__ float g0_of(float p, float d) { return p > 0.f ? d * (1.f - p * p) : 0.f; }
+// G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter
+// gradients are ill-conditioned sums of G0 (zero-sum projection), so float32 rounding inside this
+// product (dpred, tanh, 1-p^2) costs ~1e-5 relative on the worst gradient (scratch/precision_probe.py)
+__device__ __forceinline__ float g0_of(double p, double d) { return p > 0.0 ? (float)(d * (1.0 - p * p)) : 0.f; }
 
 // tile geometry shared by host and device
 struct TileGeo {

@@ -124,21 +124,26 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
         for (int zo = 0; zo < kRZ; ++zo) {
             const int gz = z0 + zo;
             if (gz >= p.Z) break;
-            float o[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanhf(acc[zo][r]) : 0.f;
             const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
             if (p.out_f64) {
+                // float64 callers (the reference's convention) get tanh evaluated in double: the backward
+                // differentiates through this value and its gradients are ill-conditioned (stencil_common.cuh)
+                double o[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanh((double)acc[zo][r]) : 0.0;
                 double* out = reinterpret_cast<double*>(p.pred) + idx;
                 if (vec) {
-                    reinterpret_cast<double2*>(out)[0] = make_double2((double)o[0], (double)o[1]);
-                    reinterpret_cast<double2*>(out)[1] = make_double2((double)o[2], (double)o[3]);
+                    reinterpret_cast<double2*>(out)[0] = make_double2(o[0], o[1]);
+                    reinterpret_cast<double2*>(out)[1] = make_double2(o[2], o[3]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        if (gy + r < p.Y) out[r] = (double)o[r];
+                        if (gy + r < p.Y) out[r] = o[r];
                 }
             } else {
+                float o[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanhf(acc[zo][r]) : 0.f;
                 float* out = reinterpret_cast<float*>(p.pred) + idx;
                 if (vec) {
                     *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);

@@ -25,11 +25,10 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p, int
                 }
             }
         }
-        const float o = s > 0.f ? tanhf(s) : 0.f;
         if (p.out_f64)
-            reinterpret_cast<double*>(p.pred)[i] = (double)o;
+            reinterpret_cast<double*>(p.pred)[i] = s > 0.f ? tanh((double)s) : 0.0;
         else
-            reinterpret_cast<float*>(p.pred)[i] = o;
+            reinterpret_cast<float*>(p.pred)[i] = s > 0.f ? tanhf(s) : 0.f;
     }
 }
 
@@ -46,9 +45,9 @@ __global__ void __launch_bounds__(256) bwd_generic_kernel(const BwdParams p, int
         const long long b = i / ((long long)p.Y * p.X * p.Z);
         const int gz = z + oz, gx = x + ox, gy = y + oy;
         if (gz < 0 || gz >= p.Z || gx < 0 || gx >= p.X || gy < 0 || gy >= p.Y) continue;
-        const float pv = p.pred_f64 ? (float)reinterpret_cast<const double*>(p.pred)[i] : reinterpret_cast<const float*>(p.pred)[i];
-        if (!(pv > 0.f)) continue;
-        const float dv = p.dpred_f64 ? (float)reinterpret_cast<const double*>(p.dpred)[i] : reinterpret_cast<const float*>(p.dpred)[i];
+        const double pv = p.pred_f64 ? reinterpret_cast<const double*>(p.pred)[i] : (double)reinterpret_cast<const float*>(p.pred)[i];
+        if (!(pv > 0.0)) continue;
+        const double dv = p.dpred_f64 ? reinterpret_cast<const double*>(p.dpred)[i] : (double)reinterpret_cast<const float*>(p.dpred)[i];
         s += (double)(g0_of(pv, dv) * __ldg(p.x + ((b * p.Z + gz) * p.X + gx) * p.Y + gy));
     }
     s = warp_sum(s);

@@ -43,6 +43,7 @@ class ObserverSpec:
     lambda_sum_order: Optional[Sequence[int]] = None  # operator ids in lambdas_dict order
     last_lambda: int = -1                # operator id; -1 = none
     observer: bool = True                # False: bare kernels (no lambdas)
+    unused: frozenset = frozenset()      # param_ptrs indices that do not enter the graph (grad None, not 0)
 
     def n_param_ptrs(self) -> int:
         n = sum(N_PARAMS[k] for k in self.kinds)
@@ -90,6 +91,21 @@ def _snapshot_ptr_array(snapshot: torch.Tensor):
     for i in range(n):
         arr[i] = base + 4 * i
     return arr
+
+
+def unused_cone_params(kind: int, hc: int, kz: int, base: int) -> set:
+    """Parameters of a cone/arrow operator that do not enter the reference's autograd graph for this
+    int(apex): with hc == 0 there is no cylinder plane (arrow: `radius` unused; cone_kernel: `sigma`
+    unused), with hc == kz there is no cone slice (`cone_inc`, `cone_radius` unused).  The reference
+    leaves their .grad at None; so do we.  Order: apex, cone_inc, cone_radius, radius, sigma."""
+    out = set()
+    if kind not in (2, 3):
+        return out
+    if hc <= 0:
+        out.add(base + (3 if kind == 3 else 4))
+    if hc >= kz:
+        out.update((base + 1, base + 2))
+    return out
 
 
 # ------------------------------------------------------------------------------- synthesis
