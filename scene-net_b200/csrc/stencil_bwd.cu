@@ -4,8 +4,9 @@
 // autograd runs for SCENE_Net.py:325-337.  W is ONE T-vector (not G of them): the per-
 // operator gradients are lambda_g * W (synth.cu::sn_scenenet_param_grads).
 //
-// Persistent CTAs walk 8 x TX x TY voxel tiles (static round-robin => deterministic).  Per
-// tile: x halo by one TMA load, G0 computed on the fly from pred/dpred into shared memory.
+// Pass 1 (g0_kernel, HBM-bound elementwise): G0 in float64 from pred/dpred, rounded once to float32.
+// Pass 2 (stencil_bwd_kernel, FP32-bound): persistent CTAs walk 8 x TX x TY voxel tiles (static
+// round-robin => deterministic).  Per tile two TMA loads (x halo tile, G0 tile) land on one mbarrier.
 // Warp w of a CTA owns tap group (dx, z-chunk) for the whole kernel and keeps its C*KY
 // accumulators in registers; its lanes sweep the tile's 8x4 micro-tiles.  At the end every
 // warp reduces its accumulators across lanes in float64 and writes one partial row; a second
@@ -68,9 +69,39 @@ struct BwdChunkSwitch<KY, 0> {
     __device__ static __forceinline__ void run(int, float (&)[Geo<KY>::C * KY], const float*, int, const float*, int) {}
 };
 
+// G0 = dpred * (1 - pred^2) * [pred > 0]: 4 voxels per thread, all loads issued before use
+template <typename TP, typename TD>
+__global__ void __launch_bounds__(256) g0_kernel(const TP* __restrict__ pred, const TD* __restrict__ dpred,
+                                                 float* __restrict__ g0, long long n) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        double pv[4], dv[4];
+        if constexpr (sizeof(TP) == 8) {
+            const double2 a = reinterpret_cast<const double2*>(pred)[2 * i], c = reinterpret_cast<const double2*>(pred)[2 * i + 1];
+            pv[0] = a.x; pv[1] = a.y; pv[2] = c.x; pv[3] = c.y;
+        } else {
+            const float4 a = reinterpret_cast<const float4*>(pred)[i];
+            pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
+        }
+        if constexpr (sizeof(TD) == 8) {
+            const double2 a = reinterpret_cast<const double2*>(dpred)[2 * i], c = reinterpret_cast<const double2*>(dpred)[2 * i + 1];
+            dv[0] = a.x; dv[1] = a.y; dv[2] = c.x; dv[3] = c.y;
+        } else {
+            const float4 a = reinterpret_cast<const float4*>(dpred)[i];
+            dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w;
+        }
+        reinterpret_cast<float4*>(g0)[i] = make_float4(g0_of(pv[0], dv[0]), g0_of(pv[1], dv[1]), g0_of(pv[2], dv[2]), g0_of(pv[3], dv[3]));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        g0[i] = g0_of((double)pred[i], (double)dpred[i]);
+    }
+}
+
 template <int KY, int TYT>
 __global__ void __launch_bounds__(kBwdMaxWarps * 32, 2)
-stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) {
+stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap) {
     constexpr int C = Geo<KY>::C;
     constexpr int NACC = C * KY;
     constexpr int TY = TYT * 4, TX = kStencilThreads / TYT;
@@ -98,7 +129,6 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
     }
     uint32_t phase = 0;
     const int zstride = g.HX * g.WS, gzstride = TX * TY;
-    const bool vec = (p.Y & 3) == 0;
 
     for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         int b, z0, x0, y0;
@@ -107,52 +137,17 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
         if (p.use_tma) {
             if (tid == 0) {
                 fence_proxy_async();
-                mbar_arrive_expect_tx(bar, (uint32_t)halo_floats * 4u);
+                mbar_arrive_expect_tx(bar, (uint32_t)(halo_floats + kRZ * TX * TY) * 4u);
                 tma_load_4d(sx, &tmap, bar, y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+                tma_load_4d(sg, &gmap, bar, y0, x0, z0, b);
             }
         } else {
             load_halo_plain(sx, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, nthreads);
-        }
-        // G0 tile: 4 consecutive y per thread per step
-        for (int i = tid; i < kRZ * TX * TYT; i += nthreads) {
-            const int y4 = i % TYT, xx = (i / TYT) % TX, zz = i / (TYT * TX);
-            const int gz = z0 + zz, gx = x0 + xx, gy = y0 + 4 * y4;
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gz < p.Z && gx < p.X && gy < p.Y) {
-                const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
-                double pv[4], dv[4];
-                if (vec) {
-                    if (p.pred_f64) {
-                        const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[0];
-                        const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.pred) + idx)[1];
-                        pv[0] = a.x; pv[1] = a.y; pv[2] = c.x; pv[3] = c.y;
-                    } else {
-                        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pred) + idx);
-                        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
-                    }
-                    if (p.dpred_f64) {
-                        const double2 a = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[0];
-                        const double2 c = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.dpred) + idx)[1];
-                        dv[0] = a.x; dv[1] = a.y; dv[2] = c.x; dv[3] = c.y;
-                    } else {
-                        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dpred) + idx);
-                        dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const bool ok = gy + r < p.Y;
-                        pv[r] = !ok ? 0.0
-                                    : (p.pred_f64 ? reinterpret_cast<const double*>(p.pred)[idx + r]
-                                                  : (double)reinterpret_cast<const float*>(p.pred)[idx + r]);
-                        dv[r] = !ok ? 0.0
-                                    : (p.dpred_f64 ? reinterpret_cast<const double*>(p.dpred)[idx + r]
-                                                   : (double)reinterpret_cast<const float*>(p.dpred)[idx + r]);
-                    }
-                }
-                o = make_float4(g0_of(pv[0], dv[0]), g0_of(pv[1], dv[1]), g0_of(pv[2], dv[2]), g0_of(pv[3], dv[3]));
+            for (int i = tid; i < kRZ * TX * TY; i += nthreads) {
+                const int yy = i % TY, xx = (i / TY) % TX, zz = i / (TY * TX);
+                const int gz = z0 + zz, gx = x0 + xx, gy = y0 + yy;
+                sg[i] = (gz < p.Z && gx < p.X && gy < p.Y) ? __ldg(p.g0 + (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy) : 0.f;
             }
-            *reinterpret_cast<float4*>(sg + (zz * TX + xx) * TY + 4 * y4) = o;
         }
         __syncthreads();
         if (p.use_tma) {
@@ -184,21 +179,33 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) 
     }
 }
 
-// W[t] = sum over partial rows, fixed order
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ partial, int rows, int TP, int T,
-                                                              double* __restrict__ W) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int r = 0;
-    for (; r + 3 < rows; r += 4) {
-        s0 += partial[(size_t)r * TP + t];
-        s1 += partial[(size_t)(r + 1) * TP + t];
-        s2 += partial[(size_t)(r + 2) * TP + t];
-        s3 += partial[(size_t)(r + 3) * TP + t];
+// W[t] = sum over partial rows in a fixed order (deterministic): block = 32 taps x 32 row groups
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partial, int rows, int TP, int T,
+                                                               double* __restrict__ W) {
+    __shared__ double red[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int t = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    if (t < T) {
+        // independent loads first (memory-level parallelism), then a fixed-order sum
+        double v[16];
+        int r = ty;
+        while (r < rows) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (r + 32 * i < rows) ? partial[(size_t)(r + 32 * i) * TP + t] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s += v[i];
+            r += 32 * 16;
+        }
     }
-    for (; r < rows; ++r) s0 += partial[(size_t)r * TP + t];
-    W[t] = (s0 + s1) + (s2 + s3);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && t < T) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a += red[i][tx];
+        W[t] = a;
+    }
 }
 
 struct BwdPlan {
@@ -227,25 +234,51 @@ static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
     return pl;
 }
 
+static inline int64_t g0_bytes(int B, int Z, int X, int Y) { return (((int64_t)B * Z * X * Y * 4) + 255) & ~(int64_t)255; }
+
+static int launch_g0(const BwdParams& p, float* g0, cudaStream_t stream) {
+    const long long n = (long long)p.B * p.Z * p.X * p.Y;
+    long long blocks = ceil_div64(n / 4 + 1, 256);
+    const int grid = (int)(blocks > (long long)kNumSMs * 16 ? (long long)kNumSMs * 16 : blocks);
+    if (p.pred_f64 && p.dpred_f64)
+        g0_kernel<double, double><<<grid, 256, 0, stream>>>((const double*)p.pred, (const double*)p.dpred, g0, n);
+    else if (p.pred_f64)
+        g0_kernel<double, float><<<grid, 256, 0, stream>>>((const double*)p.pred, (const float*)p.dpred, g0, n);
+    else if (p.dpred_f64)
+        g0_kernel<float, double><<<grid, 256, 0, stream>>>((const float*)p.pred, (const double*)p.dpred, g0, n);
+    else
+        g0_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)p.pred, (const float*)p.dpred, g0, n);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
 template <int KY, int TYT>
 static int launch_bwd(BwdParams p, double* W, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     const BwdPlan pl = plan_bwd<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     if (pl.smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
-    if ((int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
+    const int64_t gb = g0_bytes(p.B, p.Z, p.X, p.Y);
+    if (gb + (int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
+    if ((((uintptr_t)p.pred) | ((uintptr_t)p.dpred)) & 15) return SN_ERR_ALIGN;
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
-    CUtensorMap tmap;
-    p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
-    p.partial = reinterpret_cast<double*>(ws);
+    float* g0 = reinterpret_cast<float*>(ws);
+    p.g0 = g0;
+    p.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + gb);
+    int rc = launch_g0(p, g0, stream);
+    if (rc) return rc;
+    CUtensorMap tmap, gmap;
+    const bool ok_x = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS);
+    const bool ok_g = make_grid_tmap(&gmap, g0, p.B, p.Z, p.X, p.Y, kRZ, g.TX, g.TY);
+    p.use_tma = (ok_x && ok_g) ? 1 : 0;
     p.ncombos = pl.ncombos;
     p.combos_per_cta = pl.combos_per_cta;
     p.TP = pl.TP;
     auto kern = stencil_bwd_kernel<KY, TYT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    kern<<<dim3(pl.grid_x, pl.grid_y), pl.combos_per_cta * 32, pl.smem, stream>>>(p, tmap);
+    kern<<<dim3(pl.grid_x, pl.grid_y), pl.combos_per_cta * 32, pl.smem, stream>>>(p, tmap, gmap);
     SN_LAUNCH_CHECK();
     const int T = p.kz * p.kx * KY;
-    reduce_partials_kernel<<<ceil_div(T, 128), 128, 0, stream>>>(p.partial, pl.grid_x, pl.TP, T, W);
+    reduce_partials_kernel<<<ceil_div(T, 32), dim3(32, 32), 0, stream>>>(p.partial, pl.grid_x, pl.TP, T, W);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -259,7 +292,7 @@ static int dispatch_bwd_ty(const BwdParams& p, double* W, void* ws, int64_t wsb,
 template <int KY>
 static int64_t ws_bytes_ty(int B, int Z, int X, int Y, int kz, int kx) {
     const BwdPlan pl = Y > 32 ? plan_bwd<KY, 16>(B, Z, X, Y, kz, kx) : plan_bwd<KY, 8>(B, Z, X, Y, kz, kx);
-    return (int64_t)pl.grid_x * pl.TP * 8;
+    return g0_bytes(B, Z, X, Y) + (int64_t)pl.grid_x * pl.TP * 8;
 }
 
 }  // namespace sn

@@ -45,6 +45,7 @@ struct BwdParams {
     const float* x;
     const void* pred;
     const void* dpred;
+    const float* g0;  // [B,1,Z,X,Y] float32 (workspace)
     double* partial;  // [gridDim.x][TP]
     int B, Z, X, Y, kz, kx;
     int pred_f64, dpred_f64, use_tma;

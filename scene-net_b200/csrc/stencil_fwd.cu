@@ -126,11 +126,11 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
             if (gz >= p.Z) break;
             const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
             if (p.out_f64) {
-                // float64 callers (the reference's convention) get tanh evaluated in double: the backward
-                // differentiates through this value and its gradients are ill-conditioned (stencil_common.cuh)
+                // tanhf is enough: a float64 tanh here costs ~27% of the kernel's instructions and buys nothing
+                // measurable (scratch/precision_probe.py: the float32 rounding of G0 in the backward dominates)
                 double o[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanh((double)acc[zo][r]) : 0.0;
+                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? (double)tanhf(acc[zo][r]) : 0.0;
                 double* out = reinterpret_cast<double*>(p.pred) + idx;
                 if (vec) {
                     reinterpret_cast<double2*>(out)[0] = make_double2(o[0], o[1]);

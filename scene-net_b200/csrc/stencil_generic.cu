@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p, int
             }
         }
         if (p.out_f64)
-            reinterpret_cast<double*>(p.pred)[i] = s > 0.f ? tanh((double)s) : 0.0;
+            reinterpret_cast<double*>(p.pred)[i] = s > 0.f ? (double)tanhf(s) : 0.0;
         else
             reinterpret_cast<float*>(p.pred)[i] = s > 0.f ? tanhf(s) : 0.f;
     }

@@ -206,6 +206,10 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
         dpred = dpred.to(torch.float32)
     dpred = dpred.contiguous()
     pred = pred.contiguous()
+    if dpred.data_ptr() % 16:  # vector loads in the G0 pass
+        dpred = dpred.clone()
+    if pred.data_ptr() % 16:
+        pred = pred.clone()
     W = torch.empty((kz, kx, ky), dtype=torch.float64, device=x32.device)
     if x32.numel() == 0:
         return W.zero_()
