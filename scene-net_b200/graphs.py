@@ -54,20 +54,25 @@ class GraphedStep:
     def _step(self):
         if self.x_host is not None:
             self.x.copy_(self.x_host, non_blocking=True)
-        for p in self.params:
-            p.grad = None
         self.pred = self.model(self.x)
+        # torch.autograd.grad instead of .backward(): no AccumulateGrad nodes take part, so parameters that
+        # were already used eagerly (their AccumulateGrad lives on the legacy stream) cannot break the capture
         if self.loss_fn is not None:
             self.loss = self.loss_fn(self.pred)
-            self.loss.backward()
+            grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
         else:
-            self.pred.backward(self.dpred)
+            grads = torch.autograd.grad(self.pred, self.params, grad_outputs=self.dpred, allow_unused=True)
+        self.grads = list(grads)
+        for p, g in zip(self.params, grads):
+            p.grad = g
         if self.post_backward is not None:
             self.post_backward()
         if self.grads_host is not None:
-            self.flat_grads = torch.stack([p.grad.reshape(()) for p in self.params])
+            self.flat_grads = torch.stack([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(()) for p in self.params])
             self.grads_host.copy_(self.flat_grads, non_blocking=True)
 
     def replay(self):
         self.graph.replay()
+        for p, g in zip(self.params, self.grads):  # several GraphedSteps may share a model: re-bind this one's grads
+            p.grad = g
         return self.pred
