@@ -11,6 +11,7 @@
 // accumulators in registers; its lanes sweep the tile's 8x4 micro-tiles.  At the end every
 // warp reduces its accumulators across lanes in float64 and writes one partial row; a second
 // tiny kernel sums the rows in fixed order (no floating-point atomics anywhere).
+#include <stdlib.h>
 #include "stencil_common.cuh"
 #include "tma_host.cuh"
 
@@ -129,6 +130,9 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
     }
     uint32_t phase = 0;
     const int zstride = g.HX * g.WS, gzstride = TX * TY;
+    // co-resident CTAs (blockIdx.x, +148, +296, ... land on the same SM) start out of phase so that their
+    // TMA waits do not coincide: a single-buffered CTA is idle while its tile loads
+    if (p.stagger_ns > 0) __nanosleep((unsigned)((blockIdx.x / kNumSMs) * p.stagger_ns));
 
     for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         int b, z0, x0, y0;
@@ -272,6 +276,10 @@ static int launch_bwd(BwdParams p, double* W, void* ws, int64_t ws_bytes, cudaSt
     p.ncombos = pl.ncombos;
     p.combos_per_cta = pl.combos_per_cta;
     p.TP = pl.TP;
+    {
+        const char* e = getenv("SN_BWD_STAGGER_NS");
+        p.stagger_ns = e ? atoi(e) : 0;
+    }
     auto kern = stencil_bwd_kernel<KY, TYT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_rc(e);

@@ -50,6 +50,7 @@ struct BwdParams {
     int B, Z, X, Y, kz, kx;
     int pred_f64, dpred_f64, use_tma;
     int ncombos, combos_per_cta, TP;
+    int stagger_ns;
 };
 
 // G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter

@@ -3,7 +3,7 @@
 // relu(tanh)): by linearity the G convolutions collapse into ONE T-tap stencil with
 // Kstar = sum_g lambda_g K_g (built by synth.cu).
 //
-// One CTA = one 8 x TX x TY output tile.  The halo tile is staged in shared memory by a
+// One 8 x TX x TY output tile at a time per CTA.  The halo tile is staged in shared memory by a
 // single TMA load (cp.async.bulk.tensor.4d; out-of-bounds -> 0 == 'same' zero padding), each
 // thread keeps an 8 x 4 register block of outputs and walks the taps with a runtime loop over
 // dx and fully unrolled (z-chunk x KY) bodies.  Bound: FP32 pipe (2*T flop/voxel vs 8 B/voxel).
@@ -59,32 +59,40 @@ struct FwdChunkSwitch<KY, 0> {
     __device__ static __forceinline__ void run(int, float (&)[kRZ][4], const float*, int, const float*) {}
 };
 
+// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... with a
+// two-stage TMA pipeline: the halo of tile k+2 is in flight while tile k+1 waits ready and tile k
+// is being computed.  (The first version launched one CTA per tile: all CTAs of a wave waited for
+// their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
 template <int KY, int TYT>
-__global__ void __launch_bounds__(kStencilThreads, 4)
+__global__ void __launch_bounds__(kStencilThreads, 2)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_floats = g.HZ * g.HX * g.WS;
-    float* sx = reinterpret_cast<float*>(smem_raw);
-    float* sk = sx + ((halo_floats + 31) & ~31);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));
-
-    int b, z0, x0, y0;
-    decode_tile(blockIdx.x, g, b, z0, x0, y0);
+    const int halo_stride = (halo_floats + 31) & ~31;
+    const int nbuf = p.use_tma ? 2 : 1;
+    float* sx0 = reinterpret_cast<float*>(smem_raw);
+    float* sk = sx0 + nbuf * halo_stride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
     const int tid = threadIdx.x;
+    const int G = gridDim.x;
 
-    if (p.use_tma) {
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            fence_barrier_init();
-            mbar_arrive_expect_tx(bar, (uint32_t)halo_floats * 4u);
-            tma_load_4d(sx, &tmap, bar, y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
-        }
-    } else {
-        load_halo_plain(sx, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
+    auto issue = [&](int tile, int buf) {  // thread 0 only
+        int b, z0, x0, y0;
+        decode_tile(tile, g, b, z0, x0, y0);
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)halo_floats * 4u);
+        tma_load_4d(sx0 + buf * halo_stride, &tmap, &bar[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+    };
+
+    if (p.use_tma && tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+        if ((int)blockIdx.x < g.ntiles) issue(blockIdx.x, 0);
+        if ((int)blockIdx.x + G < g.ntiles) issue(blockIdx.x + G, 1);
     }
-    // taps -> shared, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
+    // taps -> shared once per CTA, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
     for (int i = tid; i < p.kx * g.nchunks * CKP; i += kStencilThreads) sk[i] = 0.f;
     __syncthreads();
     const int T = p.kz * p.kx * KY;
@@ -93,64 +101,84 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
         sk[(dx * g.nchunks + dz / C) * CKP + (dz % C) * KY + dy] = __ldg(p.Kstar + t);
     }
     __syncthreads();
-    if (p.use_tma) mbar_wait(bar, 0);
 
     const int tyi = tid % TYT, txi = tid / TYT;
-    float acc[kRZ][4];
-#pragma unroll
-    for (int i = 0; i < kRZ; ++i)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
-
     const int zstride = g.HX * g.WS;
-    for (int dx = 0; dx < p.kx; ++dx) {
-        const float* sxrow = sx + (txi + dx) * g.WS + 4 * tyi;
-        for (int ch = 0; ch < g.nchunks; ++ch) {
-            const int cs = min(C, p.kz - ch * C);
-            const float* sxp = sxrow + (ch * C) * zstride;
-            const float* skp = sk + (dx * g.nchunks + ch) * CKP;
-            if (cs == C)
-                fwd_chunk<KY, C>(acc, sxp, zstride, skp);
-            else
-                FwdChunkSwitch<KY, C - 1>::run(cs, acc, sxp, zstride, skp);
-        }
-    }
+    const bool vec = ((p.Y & 3) == 0);
 
-    // epilogue: relu(tanh(s)) and store in the caller's dtype
-    const int gx = x0 + txi, gy = y0 + 4 * tyi;
-    if (gx < p.X && gy < p.Y) {
-        const bool vec = ((p.Y & 3) == 0);
+    int k = 0;
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
+        int b, z0, x0, y0;
+        decode_tile(tile, g, b, z0, x0, y0);
+        const int buf = p.use_tma ? (k & 1) : 0;
+        const float* sx = sx0 + buf * halo_stride;
+        if (p.use_tma) {
+            mbar_wait(&bar[buf], (uint32_t)(k >> 1) & 1u);
+        } else {
+            __syncthreads();  // previous tile fully consumed
+            load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
+            __syncthreads();
+        }
+
+        float acc[kRZ][4];
 #pragma unroll
-        for (int zo = 0; zo < kRZ; ++zo) {
-            const int gz = z0 + zo;
-            if (gz >= p.Z) break;
-            const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
-            if (p.out_f64) {
-                // tanhf is enough: a float64 tanh here costs ~27% of the kernel's instructions and buys nothing
-                // measurable (scratch/precision_probe.py: the float32 rounding of G0 in the backward dominates)
-                double o[4];
+        for (int i = 0; i < kRZ; ++i)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? (double)tanhf(acc[zo][r]) : 0.0;
-                double* out = reinterpret_cast<double*>(p.pred) + idx;
-                if (vec) {
-                    reinterpret_cast<double2*>(out)[0] = make_double2(o[0], o[1]);
-                    reinterpret_cast<double2*>(out)[1] = make_double2(o[2], o[3]);
-                } else {
+            for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+
+        for (int dx = 0; dx < p.kx; ++dx) {
+            const float* sxrow = sx + (txi + dx) * g.WS + 4 * tyi;
+            for (int ch = 0; ch < g.nchunks; ++ch) {
+                const int cs = min(C, p.kz - ch * C);
+                const float* sxp = sxrow + (ch * C) * zstride;
+                const float* skp = sk + (dx * g.nchunks + ch) * CKP;
+                if (cs == C)
+                    fwd_chunk<KY, C>(acc, sxp, zstride, skp);
+                else
+                    FwdChunkSwitch<KY, C - 1>::run(cs, acc, sxp, zstride, skp);
+            }
+        }
+
+        if (p.use_tma) {
+            __syncthreads();  // every thread is done reading this buffer -> refill it with tile k+2
+            if (tid == 0 && tile + 2 * G < g.ntiles) {
+                fence_proxy_async();
+                issue(tile + 2 * G, buf);
+            }
+        }
+
+        // epilogue: relu(tanh(s)) and store in the caller's dtype (overlaps the TMA just issued)
+        const int gx = x0 + txi, gy = y0 + 4 * tyi;
+        if (gx < p.X && gy < p.Y) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (gy + r < p.Y) out[r] = o[r];
-                }
-            } else {
+            for (int zo = 0; zo < kRZ; ++zo) {
+                const int gz = z0 + zo;
+                if (gz >= p.Z) break;
+                const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
+                // tanhf, not a float64 tanh: the double version cost ~27 % of the kernel's instructions and
+                // buys nothing measurable (scratch/precision_probe.py: G0's float32 rounding dominates)
                 float o[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanhf(acc[zo][r]) : 0.f;
-                float* out = reinterpret_cast<float*>(p.pred) + idx;
-                if (vec) {
-                    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
+                if (p.out_f64) {
+                    double* out = reinterpret_cast<double*>(p.pred) + idx;
+                    if (vec) {
+                        reinterpret_cast<double2*>(out)[0] = make_double2((double)o[0], (double)o[1]);
+                        reinterpret_cast<double2*>(out)[1] = make_double2((double)o[2], (double)o[3]);
+                    } else {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (gy + r < p.Y) out[r] = o[r];
+                        for (int r = 0; r < 4; ++r)
+                            if (gy + r < p.Y) out[r] = (double)o[r];
+                    }
+                } else {
+                    float* out = reinterpret_cast<float*>(p.pred) + idx;
+                    if (vec) {
+                        *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (gy + r < p.Y) out[r] = o[r];
+                    }
                 }
             }
         }
@@ -161,15 +189,20 @@ template <int KY, int TYT>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
     FwdParams p = p0;
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
-    const int halo_floats = g.HZ * g.HX * g.WS;
-    const size_t smem = (size_t)(((halo_floats + 31) & ~31) + ((p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31)) * 4 + 16;
-    if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
+    const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
+    const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
     CUtensorMap tmap;
     p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
+    size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
+    if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
+    if (!p.use_tma) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
+    if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     auto kern = stencil_fwd_kernel<KY, TYT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    kern<<<g.ntiles, kStencilThreads, smem, stream>>>(p, tmap);
+    const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
+    const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
+    kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
