@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libscenenet_b200.so")
+LIB_PATH = os.environ.get("SCENENET_B200_LIB", os.path.join(PKG, "libscenenet_b200.so"))  # override: experiments only
 
 SN_F32, SN_F64 = 0, 1
 SN_MAX_GENEOS = 16

@@ -1,0 +1,6 @@
+// tap-gradient stencil, kernels with ky = 5 (see stencil_bwd_impl.cuh)
+#include "stencil_bwd_impl.cuh"
+namespace sn {
+int stencil_bwd_ky5(const BwdParams& p, void* ws, int64_t wsb, int* rows, int* TP, cudaStream_t s) { return stencil_bwd_ky<5>(p, ws, wsb, rows, TP, s); }
+int64_t stencil_bwd_ws_ky5(int B, int Z, int X, int Y, int kz, int kx) { return stencil_bwd_ws_ky<5>(B, Z, X, Y, kz, kx); }
+}  // namespace sn

@@ -39,6 +39,7 @@ struct FwdParams {
     void* pred;
     int B, Z, X, Y, kz, kx;
     int out_f64, use_tma;
+    int dbg;  // debugging/profiling switches (SN_FWD_DBG): 1 = no stores, 2 = no tanh, 4 = no TMA
 };
 
 struct BwdParams {
@@ -50,7 +51,7 @@ struct BwdParams {
     int B, Z, X, Y, kz, kx;
     int pred_f64, dpred_f64, use_tma;
     int ncombos, combos_per_cta, TP;
-    int stagger_ns;
+    int Q, nstage;  // warps per tap group; TMA pipeline stages
 };
 
 // G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter

@@ -7,213 +7,19 @@
 // single TMA load (cp.async.bulk.tensor.4d; out-of-bounds -> 0 == 'same' zero padding), each
 // thread keeps an 8 x 4 register block of outputs and walks the taps with a runtime loop over
 // dx and fully unrolled (z-chunk x KY) bodies.  Bound: FP32 pipe (2*T flop/voxel vs 8 B/voxel).
+#include <stdlib.h>
 #include "stencil_common.cuh"
-#include "tma_host.cuh"
 
 namespace sn {
-
-template <int KY, int CS>
-__device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __restrict__ sxp, int zstride,
-                                          const float* __restrict__ skp) {
-    constexpr int WN = Geo<KY>::WN;
-    constexpr int NT = round4(CS * KY);
-    float tap[NT];
-#pragma unroll
-    for (int i = 0; i < NT / 4; ++i) {
-        const float4 v = reinterpret_cast<const float4*>(skp)[i];
-        tap[4 * i] = v.x; tap[4 * i + 1] = v.y; tap[4 * i + 2] = v.z; tap[4 * i + 3] = v.w;
-    }
-#pragma unroll
-    for (int zi = 0; zi < kRZ + CS - 1; ++zi) {
-        float win[WN];
-#pragma unroll
-        for (int i = 0; i < WN / 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(sxp + zi * zstride + 4 * i);
-            win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
-        }
-#pragma unroll
-        for (int dzl = 0; dzl < CS; ++dzl) {
-            const int zo = zi - dzl;
-            if (zo >= 0 && zo < kRZ) {
-#pragma unroll
-                for (int dy = 0; dy < KY; ++dy) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[zo][r] = fmaf(win[Geo<KY>::OFF + r + dy], tap[dzl * KY + dy], acc[zo][r]);
-                }
-            }
-        }
-    }
-}
-
-template <int KY, int CS>
-struct FwdChunkSwitch {
-    __device__ static __forceinline__ void run(int cs, float (&acc)[kRZ][4], const float* sxp, int zstride, const float* skp) {
-        if (cs == CS)
-            fwd_chunk<KY, CS>(acc, sxp, zstride, skp);
-        else
-            FwdChunkSwitch<KY, CS - 1>::run(cs, acc, sxp, zstride, skp);
-    }
-};
-template <int KY>
-struct FwdChunkSwitch<KY, 0> {
-    __device__ static __forceinline__ void run(int, float (&)[kRZ][4], const float*, int, const float*) {}
-};
-
-// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... with a
-// two-stage TMA pipeline: the halo of tile k+2 is in flight while tile k+1 waits ready and tile k
-// is being computed.  (The first version launched one CTA per tile: all CTAs of a wave waited for
-// their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
-template <int KY, int TYT>
-__global__ void __launch_bounds__(kStencilThreads, 2)
-stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
-    constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
-    const int halo_floats = g.HZ * g.HX * g.WS;
-    const int halo_stride = (halo_floats + 31) & ~31;
-    const int nbuf = p.use_tma ? 2 : 1;
-    float* sx0 = reinterpret_cast<float*>(smem_raw);
-    float* sk = sx0 + nbuf * halo_stride;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
-    const int tid = threadIdx.x;
-    const int G = gridDim.x;
-
-    auto issue = [&](int tile, int buf) {  // thread 0 only
-        int b, z0, x0, y0;
-        decode_tile(tile, g, b, z0, x0, y0);
-        mbar_arrive_expect_tx(&bar[buf], (uint32_t)halo_floats * 4u);
-        tma_load_4d(sx0 + buf * halo_stride, &tmap, &bar[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
-    };
-
-    if (p.use_tma && tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_barrier_init();
-        if ((int)blockIdx.x < g.ntiles) issue(blockIdx.x, 0);
-        if ((int)blockIdx.x + G < g.ntiles) issue(blockIdx.x + G, 1);
-    }
-    // taps -> shared once per CTA, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
-    for (int i = tid; i < p.kx * g.nchunks * CKP; i += kStencilThreads) sk[i] = 0.f;
-    __syncthreads();
-    const int T = p.kz * p.kx * KY;
-    for (int t = tid; t < T; t += kStencilThreads) {
-        const int dy = t % KY, dx = (t / KY) % p.kx, dz = t / (KY * p.kx);
-        sk[(dx * g.nchunks + dz / C) * CKP + (dz % C) * KY + dy] = __ldg(p.Kstar + t);
-    }
-    __syncthreads();
-
-    const int tyi = tid % TYT, txi = tid / TYT;
-    const int zstride = g.HX * g.WS;
-    const bool vec = ((p.Y & 3) == 0);
-
-    int k = 0;
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
-        int b, z0, x0, y0;
-        decode_tile(tile, g, b, z0, x0, y0);
-        const int buf = p.use_tma ? (k & 1) : 0;
-        const float* sx = sx0 + buf * halo_stride;
-        if (p.use_tma) {
-            mbar_wait(&bar[buf], (uint32_t)(k >> 1) & 1u);
-        } else {
-            __syncthreads();  // previous tile fully consumed
-            load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
-            __syncthreads();
-        }
-
-        float acc[kRZ][4];
-#pragma unroll
-        for (int i = 0; i < kRZ; ++i)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
-
-        for (int dx = 0; dx < p.kx; ++dx) {
-            const float* sxrow = sx + (txi + dx) * g.WS + 4 * tyi;
-            for (int ch = 0; ch < g.nchunks; ++ch) {
-                const int cs = min(C, p.kz - ch * C);
-                const float* sxp = sxrow + (ch * C) * zstride;
-                const float* skp = sk + (dx * g.nchunks + ch) * CKP;
-                if (cs == C)
-                    fwd_chunk<KY, C>(acc, sxp, zstride, skp);
-                else
-                    FwdChunkSwitch<KY, C - 1>::run(cs, acc, sxp, zstride, skp);
-            }
-        }
-
-        if (p.use_tma) {
-            __syncthreads();  // every thread is done reading this buffer -> refill it with tile k+2
-            if (tid == 0 && tile + 2 * G < g.ntiles) {
-                fence_proxy_async();
-                issue(tile + 2 * G, buf);
-            }
-        }
-
-        // epilogue: relu(tanh(s)) and store in the caller's dtype (overlaps the TMA just issued)
-        const int gx = x0 + txi, gy = y0 + 4 * tyi;
-        if (gx < p.X && gy < p.Y) {
-#pragma unroll
-            for (int zo = 0; zo < kRZ; ++zo) {
-                const int gz = z0 + zo;
-                if (gz >= p.Z) break;
-                const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
-                // tanhf, not a float64 tanh: the double version cost ~27 % of the kernel's instructions and
-                // buys nothing measurable (scratch/precision_probe.py: G0's float32 rounding dominates)
-                float o[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) o[r] = acc[zo][r] > 0.f ? tanhf(acc[zo][r]) : 0.f;
-                if (p.out_f64) {
-                    double* out = reinterpret_cast<double*>(p.pred) + idx;
-                    if (vec) {
-                        reinterpret_cast<double2*>(out)[0] = make_double2((double)o[0], (double)o[1]);
-                        reinterpret_cast<double2*>(out)[1] = make_double2((double)o[2], (double)o[3]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (gy + r < p.Y) out[r] = (double)o[r];
-                    }
-                } else {
-                    float* out = reinterpret_cast<float*>(p.pred) + idx;
-                    if (vec) {
-                        *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (gy + r < p.Y) out[r] = o[r];
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int KY, int TYT>
-static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
-    FwdParams p = p0;
-    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
-    const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
-    const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
-    CUtensorMap tmap;
-    p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
-    size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
-    if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
-    if (!p.use_tma) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
-    if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
-    auto kern = stencil_fwd_kernel<KY, TYT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_rc(e);
-    const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
-    const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
-    kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
-    SN_LAUNCH_CHECK();
-    return SN_OK;
-}
-
-template <int KY>
-static int dispatch_fwd_ty(const FwdParams& p, cudaStream_t s) {
-    return p.Y > 32 ? launch_fwd<KY, 16>(p, s) : launch_fwd<KY, 8>(p, s);
-}
-
+int stencil_fwd_ky3(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky5(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky6(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky7(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky9(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky11(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky13(const FwdParams&, cudaStream_t);
+int stencil_fwd_ky15(const FwdParams&, cudaStream_t);
 int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // stencil_generic.cu
-
 }  // namespace sn
 
 extern "C" int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z, int X, int Y, int kz, int kx, int ky,
@@ -222,18 +28,18 @@ extern "C" int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z,
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
     if (pred_dtype != SN_F32 && pred_dtype != SN_F64) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
-    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0};
+    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0};
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (ky) {
-        case 3: rc = sn::dispatch_fwd_ty<3>(p, s); break;
-        case 5: rc = sn::dispatch_fwd_ty<5>(p, s); break;
-        case 6: rc = sn::dispatch_fwd_ty<6>(p, s); break;
-        case 7: rc = sn::dispatch_fwd_ty<7>(p, s); break;
-        case 9: rc = sn::dispatch_fwd_ty<9>(p, s); break;
-        case 11: rc = sn::dispatch_fwd_ty<11>(p, s); break;
-        case 13: rc = sn::dispatch_fwd_ty<13>(p, s); break;
-        case 15: rc = sn::dispatch_fwd_ty<15>(p, s); break;
+        case 3: rc = sn::stencil_fwd_ky3(p, s); break;
+        case 5: rc = sn::stencil_fwd_ky5(p, s); break;
+        case 6: rc = sn::stencil_fwd_ky6(p, s); break;
+        case 7: rc = sn::stencil_fwd_ky7(p, s); break;
+        case 9: rc = sn::stencil_fwd_ky9(p, s); break;
+        case 11: rc = sn::stencil_fwd_ky11(p, s); break;
+        case 13: rc = sn::stencil_fwd_ky13(p, s); break;
+        case 15: rc = sn::stencil_fwd_ky15(p, s); break;
         default: rc = SN_ERR_UNSUPPORTED; break;
     }
     if (rc == SN_ERR_UNSUPPORTED) rc = sn::stencil_fwd_generic(p, ky, s);
