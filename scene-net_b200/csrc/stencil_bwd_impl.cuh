@@ -88,8 +88,8 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_barrier_init();
-        if ((int)blockIdx.x < g.ntiles) issue(blockIdx.x, 0);
-        if (nstage == 2 && (int)blockIdx.x + G < g.ntiles) issue(blockIdx.x + G, 1);
+        if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
+        if (nstage == 2 && (int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
     }
     __syncthreads();
 
@@ -100,7 +100,7 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         const float* sx = s0 + buf * stage;
         const float* sg = sx + halo_stride;
         if (p.use_tma) {
-            mbar_wait(&bar[buf], (uint32_t)(nstage == 2 ? (k >> 1) : k) & 1u);
+            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(nstage == 2 ? (k >> 1) : k) & 1u);
         } else {
             int b, z0, x0, y0;
             decode_tile(tile, g, b, z0, x0, y0);
@@ -128,22 +128,33 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         if (p.use_tma) {
             __syncthreads();  // every warp is done with this stage -> refill it
             const int next = tile + nstage * G;
-            if (tid == 0 && next < g.ntiles) {
+            if (tid == 0 && next < g.ntiles && !(p.dbg & 4)) {
                 fence_proxy_async();
                 issue(next, buf);
             }
         }
     }
 
-    // cross-lane reduction in float64; one partial row per (CTA column, q)
+    // cross-lane reduction in float64, then the Q warps of a tap group are combined through shared memory in a
+    // fixed order (q = 0,1,..): one partial row per CTA column (blockIdx.x)
+    const int cs = (REM == 0 || ch < nfull) ? C : REM;
+    double* sred = reinterpret_cast<double*>(smem_raw);  // [warps][NACC]; the tile stages are dead by now
+    __syncthreads();
     if (active) {
-        const int cs = (REM == 0 || ch < nfull) ? C : REM;
-        double* row = p.partial + ((size_t)blockIdx.x * Q + q) * p.TP;
 #pragma unroll
         for (int i = 0; i < NACC; ++i) {
             const double s = warp_sum((double)acc[i]);
+            if (lane == 0) sred[warp * NACC + i] = s;
+        }
+    }
+    __syncthreads();
+    if (active && q == 0) {
+        double* row = p.partial + (size_t)blockIdx.x * p.TP;
+        for (int i = lane; i < NACC; i += 32) {
+            double s = sred[warp * NACC + i];
+            for (int j = 1; j < Q; ++j) s += sred[(warp + j) * NACC + i];
             const int dzl = i / KY, dy = i % KY;
-            if (lane == 0 && dzl < cs) row[((ch * C + dzl) * p.kx + dx) * KY + dy] = s;
+            if (dzl < cs) row[((ch * C + dzl) * p.kx + dx) * KY + dy] = s;
         }
     }
 }
@@ -182,7 +193,7 @@ static int launch_bwd(BwdParams p, void* ws, int64_t ws_bytes, int* rows_out, cu
     const BwdPlan pl = plan_bwd<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     if (pl.smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     const int64_t gb = g0_bytes(p.B, p.Z, p.X, p.Y);
-    if (gb + (int64_t)pl.grid_x * pl.Q * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
+    if (gb + (int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     float* g0 = reinterpret_cast<float*>(ws);
     p.g0 = g0;
@@ -196,12 +207,16 @@ static int launch_bwd(BwdParams p, void* ws, int64_t ws_bytes, int* rows_out, cu
     p.TP = pl.TP;
     p.Q = pl.Q;
     p.nstage = p.use_tma ? pl.nstage : 1;
+    {
+        const char* e = getenv("SN_BWD_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     auto kern = stencil_bwd_kernel<KY, TYT, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_rc(e);
     kern<<<dim3(pl.grid_x, pl.grid_y), pl.threads, pl.smem, stream>>>(p, tmap, gmap);
     SN_LAUNCH_CHECK();
-    *rows_out = pl.grid_x * pl.Q;
+    *rows_out = pl.grid_x;
     return SN_OK;
 }
 
@@ -228,7 +243,7 @@ int stencil_bwd_ky(const BwdParams& p, void* ws, int64_t wsb, int* rows, int* TP
 template <int KY>
 int64_t stencil_bwd_ws_ky(int B, int Z, int X, int Y, int kz, int kx) {
     const BwdPlan pl = Y > 32 ? plan_bwd<KY, 16>(B, Z, X, Y, kz, kx) : plan_bwd<KY, 8>(B, Z, X, Y, kz, kx);
-    return g0_bytes(B, Z, X, Y) + (int64_t)pl.grid_x * pl.Q * pl.TP * 8;
+    return g0_bytes(B, Z, X, Y) + (int64_t)pl.grid_x * pl.TP * 8;
 }
 
 }  // namespace sn

@@ -52,6 +52,7 @@ struct BwdParams {
     int pred_f64, dpred_f64, use_tma;
     int ncombos, combos_per_cta, TP;
     int Q, nstage;  // warps per tap group; TMA pipeline stages
+    int dbg;        // profiling switch (SN_BWD_DBG): 4 = no TMA
 };
 
 // G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter

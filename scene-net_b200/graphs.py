@@ -18,6 +18,10 @@ import torch
 class GraphedStep:
     """forward + backward of `model` on static buffers, replayable.
 
+    Capture BEFORE running an eager backward of the same parameters on the default stream (a torch
+    restriction: autograd bookkeeping created on the legacy stream cannot be joined from a capturing
+    stream), or run those eager steps inside a side stream.
+
     x:        static device input [B,1,Z,X,Y] (float32/float64); refill it (or `x_host`) between replays
     dpred:    static upstream gradient (same shape), or None when `loss_fn(pred) -> scalar` is given
     x_host:   optional pinned host tensor; when given every replay starts with x.copy_(x_host) (H2D)

@@ -351,17 +351,22 @@ def test_graphed_step_matches_eager():
     x, _ = mo.synthetic_grids(4, (32, 32, 32), seed=3)
     x = x.to(DEV)
     dp = torch.randn(x.shape, generator=torch.Generator().manual_seed(9), dtype=torch.float64).to(DEV)
-    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
-    pred = m(x)
-    pred.backward(dp)
-    ref_pred = pred.detach().clone()
-    ref_g = [p.grad.clone() for p in m.parameters() if p.requires_grad]
+    # capture first (torch requires that no eager backward has touched these parameters on the legacy stream)
+    mg = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
     xs = torch.zeros_like(x)
-    gs = GraphedStep(m, xs, dpred=dp)
+    gs = GraphedStep(mg, xs, dpred=dp)
     xs.copy_(x)
+    outs = []
     for _ in range(2):
         out = gs.replay()
         torch.cuda.synchronize()
-        assert torch.equal(out, ref_pred)
-        for p, r in zip(gs.params, ref_g):
-            assert torch.equal(p.grad, r)
+        outs.append((out.clone(), [p.grad.clone() for p in gs.params]))
+    # eager reference on a fresh, identical model
+    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+    pred = m(x)
+    pred.backward(dp)
+    ref_g = [p.grad for p in m.parameters() if p.requires_grad]
+    for out, grads in outs:
+        assert torch.equal(out, pred.detach())
+        for g, r in zip(grads, ref_g):
+            assert torch.equal(g, r)
