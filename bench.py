@@ -329,11 +329,18 @@ def main():
             b.synchronize()
             return a.elapsed_time(b) / reps * 1e-3
 
+        g0s = [ops.g0(preds[i], pool[i][1]) for i in range(n_sets)]
         t_fwd = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype))
-        t_bwd = time_kernel(lambda i: ops.scenenet_bwd(x32s[i % n_sets], preds[i % n_sets], pool[i % n_sets][1], KERNEL))
+        t_g0 = time_kernel(lambda i: ops.g0(preds[i % n_sets], pool[i % n_sets][1]))
+        t_tap = time_kernel(lambda i: ops.tapgrad(x32s[i % n_sets], g0s[i % n_sets], KERNEL))   # tap-gradient kernel + row reduction
+        t_cast = time_kernel(lambda i: ops.cast_f32(pool[i % n_sets][0])) if io_dtype == torch.float64 else 0.0
         fl = 2.0 * T * V
         esz = 8 if io_dtype == torch.float64 else 4
-        dom, t_dom, bytes_dom = ("stencil_bwd_kernel", t_bwd, V * (4 + 2 * esz)) if t_bwd >= t_fwd else ("stencil_fwd_kernel", t_fwd, V * (4 + esz))
+        if t_tap >= t_fwd:
+            dom, t_dom, bytes_dom = "stencil_bwd_kernel", t_tap, V * 8
+        else:
+            dom, t_dom, bytes_dom = "stencil_fwd_kernel", t_fwd, V * (4 + esz)
+        g0_bytes = V * (2 * esz + 4)
         roof = {
             "bound": "fp32", "kernel": dom, "achieved": fl / t_dom / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": fl / t_dom / 1e12 / peak_tf, "traffic": None,
@@ -342,7 +349,9 @@ def main():
             "hbm": {"achieved": bytes_dom / t_dom / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": bytes_dom / t_dom / 1e9 / hbm_gbs,
                     "peak_source": hbm_src},
             "fwd": {"us": t_fwd * 1e6, "tflops": fl / t_fwd / 1e12, "frac": fl / t_fwd / 1e12 / peak_tf},
-            "bwd": {"us": t_bwd * 1e6, "tflops": fl / t_bwd / 1e12, "frac": fl / t_bwd / 1e12 / peak_tf},
+            "bwd_tapgrad": {"us": t_tap * 1e6, "tflops": fl / t_tap / 1e12, "frac": fl / t_tap / 1e12 / peak_tf},
+            "g0_pass": {"us": t_g0 * 1e6, "GBps": g0_bytes / t_g0 / 1e9, "hbm_frac": g0_bytes / t_g0 / 1e9 / hbm_gbs},
+            "cast_pass": ({"us": t_cast * 1e6, "GBps": V * 12 / t_cast / 1e9, "hbm_frac": V * 12 / t_cast / 1e9 / hbm_gbs} if t_cast else None),
             "step_roofline_grids_per_s": B_PER_GPU / (2 * fl / (peak_tf * 1e12)),
         }
         if not args.no_cpu_baseline and world == 1:

@@ -139,6 +139,16 @@ int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void
                     int B, int Z, int X, int Y, int kz, int kx, int ky,
                     double* W, void* ws, int64_t ws_bytes, void* stream);
 
+/* The two passes of sn_scenenet_bwd, callable on their own (measurement, fused criterions that
+ * produce G0 themselves):  G0 [n] float32 = dpred * (1 - pred^2) * [pred > 0] evaluated in float64 and
+ * rounded once;  tap gradient W[t] = sum G0 * xpad from a precomputed G0.
+ * sn_scenenet_bwd's workspace = G0 (n*4 bytes rounded up to 256) followed by the tap-gradient workspace. */
+int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpred, int dpred_dtype, int64_t n, float* g0,
+                   void* stream);
+int64_t sn_scenenet_tapgrad_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
+int sn_scenenet_tapgrad(const float* x, const float* g0, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                        double* W, void* ws, int64_t ws_bytes, void* stream);
+
 /* ======================================================================================
  * elementwise helpers
  * ====================================================================================== */

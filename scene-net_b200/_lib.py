@@ -51,6 +51,9 @@ SIGNATURES = {
     "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sn_scenenet_g0": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
+    "sn_scenenet_tapgrad_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "sn_scenenet_tapgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),
     "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

@@ -31,7 +31,7 @@ int stencil_bwd_ky13(const BwdParams&, void*, int64_t, int*, int*, cudaStream_t)
 int64_t stencil_bwd_ws_ky13(int, int, int, int, int, int);
 int stencil_bwd_ky15(const BwdParams&, void*, int64_t, int*, int*, cudaStream_t);
 int64_t stencil_bwd_ws_ky15(int, int, int, int, int, int);
-int stencil_bwd_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream);  // stencil_generic.cu
+int stencil_tapgrad_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream);  // stencil_generic.cu
 
 // G0 = dpred * (1 - pred^2) * [pred > 0]: 4 voxels per thread, all loads issued before use
 template <typename TP, typename TD>
@@ -94,8 +94,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __r
 
 static inline int64_t g0_bytes_(int B, int Z, int X, int Y) { return (((int64_t)B * Z * X * Y * 4) + 255) & ~(int64_t)255; }
 
-static int launch_g0(const BwdParams& p, float* g0, cudaStream_t stream) {
-    const long long n = (long long)p.B * p.Z * p.X * p.Y;
+static int launch_g0(const BwdParams& p, long long n, float* g0, cudaStream_t stream) {
     long long blocks = ceil_div64(n / 4 + 1, 256);
     const int grid = (int)(blocks > (long long)kNumSMs * 16 ? (long long)kNumSMs * 16 : blocks);
     if (p.pred_f64 && p.dpred_f64)
@@ -112,8 +111,7 @@ static int launch_g0(const BwdParams& p, float* g0, cudaStream_t stream) {
 
 }  // namespace sn
 
-extern "C" int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky) {
-    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+static int64_t tapgrad_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
     switch (ky) {
         case 3: return sn::stencil_bwd_ws_ky3(B, Z, X, Y, kz, kx);
         case 5: return sn::stencil_bwd_ws_ky5(B, Z, X, Y, kz, kx);
@@ -126,31 +124,44 @@ extern "C" int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, i
         default: return 256;  // generic path needs no workspace
     }
 }
+static bool fast_ky(int ky) { return ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15; }
 
-extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
-                               int B, int Z, int X, int Y, int kz, int kx, int ky, double* W, void* ws, int64_t ws_bytes,
-                               void* stream) {
-    if (!x || !pred || !dpred || !W) return SN_ERR_BAD_ARG;
+extern "C" int64_t sn_scenenet_tapgrad_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky) {
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    return tapgrad_ws(B, Z, X, Y, kz, kx, ky);
+}
+
+extern "C" int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    return sn::g0_bytes_(B, Z, X, Y) + tapgrad_ws(B, Z, X, Y, kz, kx, ky);
+}
+
+extern "C" int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpred, int dpred_dtype, int64_t n, float* g0,
+                              void* stream) {
+    if (!pred || !dpred || !g0 || n < 1) return SN_ERR_BAD_ARG;
     if ((pred_dtype != SN_F32 && pred_dtype != SN_F64) || (dpred_dtype != SN_F32 && dpred_dtype != SN_F64))
         return SN_ERR_BAD_ARG;
+    if ((((uintptr_t)pred) | ((uintptr_t)dpred) | ((uintptr_t)g0)) & 15) return SN_ERR_ALIGN;
+    sn::BwdParams p{};
+    p.pred = pred; p.dpred = dpred;
+    p.B = 1; p.Z = 1; p.X = 1; p.Y = 1;
+    p.pred_f64 = pred_dtype == SN_F64; p.dpred_f64 = dpred_dtype == SN_F64;
+    return sn::launch_g0(p, n, g0, (cudaStream_t)stream);
+}
+
+extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                                   double* W, void* ws, int64_t ws_bytes, void* stream) {
+    if (!x || !g0 || !W) return SN_ERR_BAD_ARG;
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
     if (ws && ((uintptr_t)ws & 15)) return SN_ERR_ALIGN;
     sn::BwdParams p{};
-    p.x = x; p.pred = pred; p.dpred = dpred;
+    p.x = x; p.g0 = g0;
     p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx;
-    p.pred_f64 = pred_dtype == SN_F64; p.dpred_f64 = dpred_dtype == SN_F64;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool fast = ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15;
-    if (!fast) return sn::stencil_bwd_generic(p, ky, W, s);
+    if (!fast_ky(ky)) return sn::stencil_tapgrad_generic(p, ky, W, s);
     if (!ws) return SN_ERR_WORKSPACE;
-    if (sn::g0_bytes_(B, Z, X, Y) > ws_bytes) return SN_ERR_WORKSPACE;
-    if ((((uintptr_t)pred) | ((uintptr_t)dpred)) & 15) return SN_ERR_ALIGN;
-    // pass 1: G0 (float32) into the head of the workspace
-    int rc = sn::launch_g0(p, reinterpret_cast<float*>(ws), s);
-    if (rc) return rc;
-    // pass 2: persistent tap-gradient kernel -> partial rows
-    int rows = 0, TP = 0;
+    int rows = 0, TP = 0, rc;
     switch (ky) {
         case 3: rc = sn::stencil_bwd_ky3(p, ws, ws_bytes, &rows, &TP, s); break;
         case 5: rc = sn::stencil_bwd_ky5(p, ws, ws_bytes, &rows, &TP, s); break;
@@ -162,10 +173,23 @@ extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype,
         default: rc = sn::stencil_bwd_ky15(p, ws, ws_bytes, &rows, &TP, s); break;
     }
     if (rc) return rc;
-    // pass 3: fixed-order float64 reduction of the partial rows
-    const double* partial = reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + sn::g0_bytes_(B, Z, X, Y));
+    // fixed-order float64 reduction of the partial rows
     const int T = kz * kx * ky;
-    sn::reduce_partials_kernel<<<sn::ceil_div(T, 32), dim3(32, 32), 0, s>>>(partial, rows, TP, T, W);
+    sn::reduce_partials_kernel<<<sn::ceil_div(T, 32), dim3(32, 32), 0, s>>>(reinterpret_cast<const double*>(ws), rows, TP, T, W);
     SN_LAUNCH_CHECK();
     return SN_OK;
+}
+
+extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
+                               int B, int Z, int X, int Y, int kz, int kx, int ky, double* W, void* ws, int64_t ws_bytes,
+                               void* stream) {
+    if (!x || !pred || !dpred || !W || !ws) return SN_ERR_BAD_ARG;
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    if ((uintptr_t)ws & 15) return SN_ERR_ALIGN;
+    const int64_t gb = sn::g0_bytes_(B, Z, X, Y);
+    if (gb > ws_bytes) return SN_ERR_WORKSPACE;
+    float* g0 = reinterpret_cast<float*>(ws);
+    int rc = sn_scenenet_g0(pred, pred_dtype, dpred, dpred_dtype, (int64_t)B * Z * X * Y, g0, stream);
+    if (rc) return rc;
+    return sn_scenenet_tapgrad(x, g0, B, Z, X, Y, kz, kx, ky, W, reinterpret_cast<char*>(ws) + gb, ws_bytes - gb, stream);
 }

@@ -186,18 +186,14 @@ static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
     return pl;
 }
 
-static inline int64_t g0_bytes(int B, int Z, int X, int Y) { return (((int64_t)B * Z * X * Y * 4) + 255) & ~(int64_t)255; }
-
 template <int KY, int TYT, int REM>
 static int launch_bwd(BwdParams p, void* ws, int64_t ws_bytes, int* rows_out, cudaStream_t stream) {
     const BwdPlan pl = plan_bwd<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     if (pl.smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
-    const int64_t gb = g0_bytes(p.B, p.Z, p.X, p.Y);
-    if (gb + (int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
+    if ((int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
-    float* g0 = reinterpret_cast<float*>(ws);
-    p.g0 = g0;
-    p.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + gb);
+    const float* g0 = p.g0;
+    p.partial = reinterpret_cast<double*>(ws);
     CUtensorMap tmap, gmap;
     const bool ok_x = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS);
     const bool ok_g = make_grid_tmap(&gmap, g0, p.B, p.Z, p.X, p.Y, kRZ, g.TX, g.TY);
@@ -243,7 +239,7 @@ int stencil_bwd_ky(const BwdParams& p, void* ws, int64_t wsb, int* rows, int* TP
 template <int KY>
 int64_t stencil_bwd_ws_ky(int B, int Z, int X, int Y, int kz, int kx) {
     const BwdPlan pl = Y > 32 ? plan_bwd<KY, 16>(B, Z, X, Y, kz, kx) : plan_bwd<KY, 8>(B, Z, X, Y, kz, kx);
-    return g0_bytes(B, Z, X, Y) + (int64_t)pl.grid_x * pl.TP * 8;
+    return (int64_t)pl.grid_x * pl.TP * 8;
 }
 
 }  // namespace sn

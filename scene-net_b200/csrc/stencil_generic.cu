@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p, int
     }
 }
 
-// one CTA per tap
-__global__ void __launch_bounds__(256) bwd_generic_kernel(const BwdParams p, int ky, double* __restrict__ W) {
+// one CTA per tap (G0 precomputed)
+__global__ void __launch_bounds__(256) tapgrad_generic_kernel(const BwdParams p, int ky, double* __restrict__ W) {
     __shared__ double red[8];
     const int t = blockIdx.x;
     const int dy = t % ky, dx = (t / ky) % p.kx, dz = t / (ky * p.kx);
@@ -45,10 +45,9 @@ __global__ void __launch_bounds__(256) bwd_generic_kernel(const BwdParams p, int
         const long long b = i / ((long long)p.Y * p.X * p.Z);
         const int gz = z + oz, gx = x + ox, gy = y + oy;
         if (gz < 0 || gz >= p.Z || gx < 0 || gx >= p.X || gy < 0 || gy >= p.Y) continue;
-        const double pv = p.pred_f64 ? reinterpret_cast<const double*>(p.pred)[i] : (double)reinterpret_cast<const float*>(p.pred)[i];
-        if (!(pv > 0.0)) continue;
-        const double dv = p.dpred_f64 ? reinterpret_cast<const double*>(p.dpred)[i] : (double)reinterpret_cast<const float*>(p.dpred)[i];
-        s += (double)(g0_of(pv, dv) * __ldg(p.x + ((b * p.Z + gz) * p.X + gx) * p.Y + gy));
+        const float g = __ldg(p.g0 + i);
+        if (g == 0.f) continue;
+        s += (double)(g * __ldg(p.x + ((b * p.Z + gz) * p.X + gx) * p.Y + gy));
     }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -68,8 +67,8 @@ int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream) {
     return SN_OK;
 }
 
-int stencil_bwd_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream) {
-    bwd_generic_kernel<<<p.kz * p.kx * ky, 256, 0, stream>>>(p, ky, W);
+int stencil_tapgrad_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream) {
+    tapgrad_generic_kernel<<<p.kz * p.kx * ky, 256, 0, stream>>>(p, ky, W);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

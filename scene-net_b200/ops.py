@@ -222,6 +222,27 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
     return W
 
 
+def g0(pred: torch.Tensor, dpred: torch.Tensor) -> torch.Tensor:
+    """G0 = dpred * (1 - pred^2) * [pred > 0] as float32 (pass 1 of the backward)."""
+    out = torch.empty(pred.shape, dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        check(lib.sn_scenenet_g0(pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype], pred.numel(),
+                                 out.data_ptr(), _stream()), "sn_scenenet_g0")
+    return out
+
+
+def tapgrad(x32: torch.Tensor, g0_: torch.Tensor, kernel_size) -> torch.Tensor:
+    """W [kz,kx,ky] float64 from a precomputed G0 (pass 2 + 3 of the backward)."""
+    B, Z, X, Y = _grid_dims(x32)
+    kz, kx, ky = (int(v) for v in kernel_size)
+    W = torch.empty((kz, kx, ky), dtype=torch.float64, device=x32.device)
+    ws = _workspace(int(lib.sn_scenenet_tapgrad_workspace_bytes(B, Z, X, Y, kz, kx, ky)), x32.device)
+    with torch.cuda.device(x32.device):
+        check(lib.sn_scenenet_tapgrad(x32.data_ptr(), g0_.data_ptr(), B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _stream()), "sn_scenenet_tapgrad")
+    return W
+
+
 def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
     _need_cuda(p, "p")
     if p.dtype not in _DT:
