@@ -108,6 +108,55 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": (max(pw) if pw else None)}
 
 
+def voxel_bench(device, hbm_gbs):
+    """BASELINE metric, second half: voxelization Mpts/s (config 3 shapes: UTM-offset float64 rows x,y,z,label;
+    70 % ground sheet, 25 % vegetation blobs, 5 % tower column; scan-coherent order), counts + keep votes +
+    occupancy/target grids, through voxel_ops.voxelize_clouds (bounding box, edges, binning, finalize)."""
+    from scenenet_b200 import voxel_ops
+
+    def cloud(n, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        f64 = dict(generator=g, device=device, dtype=torch.float64)
+        n_g, n_v = int(0.70 * n), int(0.25 * n)
+        n_t = n - n_g - n_v
+        ground = torch.stack([torch.rand(n_g, **f64) * 30, torch.rand(n_g, **f64) * 30, torch.randn(n_g, **f64) * 0.3], 1)
+        cent = torch.rand((20, 3), **f64) * torch.tensor([30, 30, 9.0], device=device, dtype=torch.float64)
+        veg = cent[torch.randint(0, 20, (n_v,), generator=g, device=device)] + torch.randn((n_v, 3), **f64) * 2.0
+        tower = torch.stack([torch.randn(n_t, **f64) * 0.5 + 15, torch.randn(n_t, **f64) * 0.5 + 15, torch.rand(n_t, **f64) * 40], 1)
+        pts = torch.cat([ground, veg, tower]) + torch.tensor([544850.0, 4634550.0, 160.0], device=device, dtype=torch.float64)
+        lab = torch.cat([torch.randint(1, 13, (n_g + n_v,), generator=g, device=device).double(),
+                         torch.full((n_t,), 15.0, device=device, dtype=torch.float64)])
+        order = torch.argsort(((pts[:, 0] - 544850.0) / 2).floor() * 64 + ((pts[:, 1] - 4634550.0) / 2).floor())
+        return torch.cat([pts[order], lab[order, None]], 1).contiguous()
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    out = {}
+    for n, grid in ((1_000_000, 64), (10_000_000, 128)):
+        rows = cloud(n, 1)
+        dt = timeit(lambda: voxel_ops.voxelize_clouds(rows[:, :3], None, (grid,) * 3, rows[:, 3], [15], want=("occ", "occ_keep")))
+        alg = 56 * n + 24 * grid ** 3
+        out[f"{n // 1_000_000}M_pts_{grid}^3"] = {"Mpts_per_s": n / dt / 1e6, "us": dt * 1e6, "algorithmic_GBps": alg / dt / 1e9,
+                                                   "hbm_frac": alg / dt / 1e9 / hbm_gbs}
+        del rows
+    rows = torch.cat([cloud(60_000, s) for s in range(32)])
+    off = torch.arange(0, 33, device=device, dtype=torch.int64) * 60_000
+    dt = timeit(lambda: voxel_ops.voxelize_clouds(rows[:, :3], off, (64, 64, 64), rows[:, 3], [15], want=("occ", "occ_keep")))
+    out["batch_32x60k_pts_64^3"] = {"Mpts_per_s": 32 * 60_000 / dt / 1e6, "clouds_per_s": 32 / dt, "us": dt * 1e6}
+    out["note"] = "eager calls (8 launches); algorithmic bytes = 56 B/point + 24 B/voxel (SURVEY 8d)"
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -307,6 +356,7 @@ def main():
     # ------------------------------------------------ roofline of the two stencil kernels, timed alone with CUDA events
     roof = None
     cpu_base = None
+    vox = None
     if rank == 0:
         T = KERNEL[0] * KERNEL[1] * KERNEL[2]
         V = B_PER_GPU * GRID[0] * GRID[1] * GRID[2]
@@ -354,6 +404,7 @@ def main():
             "cast_pass": ({"us": t_cast * 1e6, "GBps": V * 12 / t_cast / 1e9, "hbm_frac": V * 12 / t_cast / 1e9 / hbm_gbs} if t_cast else None),
             "step_roofline_grids_per_s": B_PER_GPU / (2 * fl / (peak_tf * 1e12)),
         }
+        vox = voxel_bench(device, hbm_gbs)
         if not args.no_cpu_baseline and world == 1:
             v, per = time_cpu(2, 3, 1)
             cpu_base = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -373,7 +424,7 @@ def main():
                        "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "note": "x from pinned host memory each step; dL/dpred resident on the device (config 2(i)); gradients read back"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "voxelize": vox,
         }
         print(json.dumps(line))
     if world > 1:
