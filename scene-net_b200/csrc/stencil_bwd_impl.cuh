@@ -42,33 +42,29 @@ __device__ __forceinline__ void bwd_chunk(float (&acc)[Geo<KY>::C * KY], const f
     }
 }
 
-// One persistent CTA per SM of NW warps (a 21st producer warp would put 6 warps on one scheduler and cap the
-// registers at 80: lane 0 of warp 0 feeds the pipeline instead).  Warp w owns tap group
-// (dx, z-chunk) = combo w / Q for the whole kernel and keeps its C*KY accumulators in registers; the Q warps of
-// a combo split a tile's 8x4 micro-tiles (Q = 4: one micro-tile per lane per tile, and the four warps of a
-// combo sit on the four schedulers).  x halo + G0 tile arrive by TMA through a full/empty mbarrier pipeline:
-// a stage is refilled as soon as all warps have released it, and no warp except the feeding one ever waits
-// for another (the first version had a __syncthreads per tile: 10 % of the warp time, profiles/r1_notes.md).
+// One persistent CTA per SM.  Warp w owns tap group (dx, z-chunk) = combo w / Q for the whole kernel and
+// keeps its C*KY accumulators in registers; the Q warps of a combo split a tile's 8x4 micro-tiles
+// between them (Q = 4: one micro-tile per lane per tile, and the four warps of a combo sit on the four
+// schedulers).  x halo + G0 tile arrive by TMA through a two-stage pipeline: tile k+2 is requested as
+// soon as every warp has finished tile k.
 template <int KY, int TYT, int REM>
 __global__ void __launch_bounds__(kBwdMaxThreads, 1)
 stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap) {
     constexpr int C = Geo<KY>::C;
     constexpr int NACC = C * KY;
-    constexpr int TY = TYT * 4, TX = kBwdMicro / TYT;
-    constexpr int MICRO = kBwdMicro;  // micro-tiles per CTA tile (z extent of a tile == kRZ)
+    constexpr int TY = TYT * 4, TX = kStencilThreads / TYT;
+    constexpr int MICRO = TX * TYT;  // micro-tiles per CTA tile (z extent of a tile == kRZ)
     constexpr int G0F = kRZ * TX * TY;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TileGeo g = make_geo<KY, TYT, kBwdMicro>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
     const int stage = halo_stride + G0F;
     const int nstage = p.nstage;
     float* s0 = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(s0 + nstage * stage);  // [2]
-    uint64_t* empty = full + 2;                                         // [2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s0 + nstage * stage);  // [2]
 
     const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31;
-    const int NW = nthreads >> 5;
     const int Q = p.Q, q = warp % Q;
     const int combo = blockIdx.y * p.combos_per_cta + warp / Q;
     const bool active = combo < p.ncombos;
@@ -80,46 +76,31 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
 
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], NW);
-        mbar_init(&empty[1], NW);
+    auto issue = [&](int tile, int buf) {  // thread 0 only
+        int b, z0, x0, y0;
+        decode_tile(tile, g, b, z0, x0, y0);
+        float* sx = s0 + buf * stage;
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)(halo_floats + G0F) * 4u);
+        tma_load_4d(sx, &tmap, &bar[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+        tma_load_4d(sx + halo_stride, &gmap, &bar[buf], y0, x0, z0, b);
+    };
+    if (p.use_tma && tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_barrier_init();
+        if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
+        if (nstage == 2 && (int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
     }
     __syncthreads();
 
     const int zstride = g.HX * g.WS, gzstride = TX * TY;
-    auto issue = [&](int tile, int buf) {  // one lane only
-        int b, z0, x0, y0;
-        decode_tile(tile, g, b, z0, x0, y0);
-        float* sx = s0 + buf * stage;
-        mbar_arrive_expect_tx(&full[buf], (uint32_t)(halo_floats + G0F) * 4u);
-        tma_load_4d(sx, &tmap, &full[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
-        tma_load_4d(sx + halo_stride, &gmap, &full[buf], y0, x0, z0, b);
-    };
-    if (p.use_tma && tid == 0) {
-        for (int j = 0; j < nstage; ++j)
-            if ((int)blockIdx.x + j * G < g.ntiles) issue(blockIdx.x + j * G, j);
-    }
-
     int k = 0;
     for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
-        const int buf = p.use_tma ? k % nstage : 0;
+        const int buf = (nstage == 2) ? (k & 1) : 0;
         const float* sx = s0 + buf * stage;
         const float* sg = sx + halo_stride;
         if (p.use_tma) {
-            if (warp == 0 && k >= 1) {
-                // feed the pipeline: tile k-1's stage is reused for tile k+nstage-1 once every warp has released it
-                const int next = tile + (nstage - 1) * G;
-                if (lane == 0 && next < g.ntiles) {
-                    const int bufn = (k - 1) % nstage;
-                    mbar_wait(&empty[bufn], (uint32_t)((k - 1) / nstage) & 1u);
-                    issue(next, bufn);
-                }
-                __syncwarp();
-            }
-            mbar_wait(&full[buf], (uint32_t)(k / nstage) & 1u);
+            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(nstage == 2 ? (k >> 1) : k) & 1u);
         } else {
             int b, z0, x0, y0;
             decode_tile(tile, g, b, z0, x0, y0);
@@ -145,8 +126,12 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
             }
         }
         if (p.use_tma) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);  // this warp is done with the stage
+            __syncthreads();  // every warp is done with this stage -> refill it
+            const int next = tile + nstage * G;
+            if (tid == 0 && next < g.ntiles && !(p.dbg & 4)) {
+                fence_proxy_async();
+                issue(next, buf);
+            }
         }
     }
 
@@ -181,8 +166,8 @@ struct BwdPlan {
 
 template <int KY, int TYT>
 static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
-    const TileGeo g = make_geo<KY, TYT, kBwdMicro>(B, Z, X, Y, kz, kx);
-    constexpr int MICRO = kBwdMicro;  // TX * TYT
+    const TileGeo g = make_geo<KY, TYT>(B, Z, X, Y, kz, kx);
+    constexpr int MICRO = kStencilThreads;  // TX * TYT
     BwdPlan pl;
     pl.ncombos = kx * g.nchunks;
     const int max_warps = kBwdMaxThreads / 32;
@@ -206,7 +191,7 @@ static int launch_bwd(BwdParams p, void* ws, int64_t ws_bytes, int* rows_out, cu
     const BwdPlan pl = plan_bwd<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     if (pl.smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     if ((int64_t)pl.grid_x * pl.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
-    const TileGeo g = make_geo<KY, TYT, kBwdMicro>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const float* g0 = p.g0;
     p.partial = reinterpret_cast<double*>(ws);
     CUtensorMap tmap, gmap;

@@ -11,8 +11,7 @@
 namespace sn {
 
 constexpr int kRZ = 8;           // z extent of a micro-tile == z extent of a CTA tile
-constexpr int kFwdMicro = 256;      // micro-tiles (= compute threads) per forward tile: 8 warps, 1 CTA per SM
-constexpr int kBwdMicro = 128;      // micro-tiles per backward tile: 4 warps' worth, split over the Q warps of a tap group
+constexpr int kStencilThreads = 128;
 
 // z-chunk (taps held in registers at once) per compile-time KY: C*KY <= 48 registers
 __host__ __device__ constexpr int cmax_for(int ky) {
@@ -39,7 +38,7 @@ struct FwdParams {
     const float* Kstar;
     void* pred;
     int B, Z, X, Y, kz, kx;
-    int out_f64, use_tma, nstage;
+    int out_f64, use_tma;
     int dbg;  // debugging/profiling switches (SN_FWD_DBG): 1 = no stores, 2 = no tanh, 4 = no TMA
 };
 
@@ -70,11 +69,11 @@ struct TileGeo {
     int plz, plx, ply;   // left extents of the halo box (ply is rounded up to 4 floats, see Geo)
 };
 
-template <int KY, int TYT, int NT>
+template <int KY, int TYT>
 __host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, int kx) {
     TileGeo g;
     g.TY = TYT * 4;
-    g.TX = NT / TYT;
+    g.TX = kStencilThreads / TYT;
     g.HZ = kRZ + kz - 1;
     g.HX = g.TX + kx - 1;
     g.WS = round4(g.TY + Geo<KY>::OFF + KY - 1);

@@ -75,144 +75,103 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
     }
 }
 
-// One persistent CTA per SM: 8 compute warps (thread = 8 x 4 register block of outputs, tile = 8 x TX x TY
-// with TX*TY/4 = 256 micro-tiles) + 1 producer warp that keeps a two-stage TMA pipeline full through
-// full/empty mbarriers.  No block-wide barrier in the tile loop: a warp releases the stage as soon as its
-// taps are done and applies relu(tanh) to the finished tile WHILE it computes the next one (two pending rows
-// after every dx iteration), so the low-IPC epilogue never runs on its own.
-// History (profiles/r1_notes.md): one CTA per tile -> all CTAs of a wave waited for their halo together;
-// 2 persistent CTAs per SM with a __syncthreads per tile -> the tanhf epilogue (10-15 us of 95) ran with the
-// FMA pipe idle.
-constexpr int kFwdThreads = kFwdMicro + 32;
-
+// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... with a
+// two-stage TMA pipeline: the halo of tile k+2 is in flight while tile k+1 waits ready and tile k
+// is being computed.  (The first version launched one CTA per tile: all CTAs of a wave waited for
+// their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
 template <int KY, int TYT, int REM>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kStencilThreads, 2)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TileGeo g = make_geo<KY, TYT, kFwdMicro>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
-    const int nstage = p.nstage;
+    const int nbuf = p.use_tma ? 2 : 1;
     float* sx0 = reinterpret_cast<float*>(smem_raw);
-    float* sk = sx0 + nstage * halo_stride;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
-    uint64_t* empty = full + 2;                                                                 // [2]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = kFwdMicro / 32;
+    float* sk = sx0 + nbuf * halo_stride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
+    const int tid = threadIdx.x;
     const int G = gridDim.x;
 
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], NW);
-        mbar_init(&empty[1], NW);
+    auto issue = [&](int tile, int buf) {  // thread 0 only
+        int b, z0, x0, y0;
+        decode_tile(tile, g, b, z0, x0, y0);
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)halo_floats * 4u);
+        tma_load_4d(sx0 + buf * halo_stride, &tmap, &bar[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+    };
+
+    if (p.use_tma && tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_barrier_init();
+        if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
+        if ((int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
     }
     // taps -> shared once per CTA, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
-    for (int i = tid; i < p.kx * g.nchunks * CKP; i += kFwdThreads) sk[i] = 0.f;
+    for (int i = tid; i < p.kx * g.nchunks * CKP; i += kStencilThreads) sk[i] = 0.f;
     __syncthreads();
     const int T = p.kz * p.kx * KY;
-    for (int t = tid; t < T; t += kFwdThreads) {
+    for (int t = tid; t < T; t += kStencilThreads) {
         const int dy = t % KY, dx = (t / KY) % p.kx, dz = t / (KY * p.kx);
         sk[(dx * g.nchunks + dz / C) * CKP + (dz % C) * KY + dy] = __ldg(p.Kstar + t);
     }
     __syncthreads();
 
-    if (p.use_tma && warp == NW) {
-        // ---- producer
-        if (lane == 0) {
-            int k = 0;
-            for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
-                const int buf = k % nstage, use = k / nstage;
-                if (use > 0) mbar_wait(&empty[buf], (uint32_t)(use - 1) & 1u);
-                int b, z0, x0, y0;
-                decode_tile(tile, g, b, z0, x0, y0);
-                mbar_arrive_expect_tx(&full[buf], (uint32_t)halo_floats * 4u);
-                tma_load_4d(sx0 + buf * halo_stride, &tmap, &full[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
-            }
-        }
-        return;
-    }
-
-    // ---- compute warps (the producer warp only gets here without TMA, as a loader)
-    const bool compute = warp < NW;
-    const int tyi = (tid % kFwdMicro) % TYT, txi = (tid % kFwdMicro) / TYT;
+    const int tyi = tid % TYT, txi = tid / TYT;
     const int zstride = g.HX * g.WS;
     const bool vec = ((p.Y & 3) == 0);
-    const int nfull = p.kz / C;
-    const int rows_per_dx = (kRZ + p.kx - 1) / p.kx;
-
-    float pend[kRZ][4];      // finished-but-not-yet-stored outputs of the previous tile
-    int npend = 0, pz = 0, pny = 0;   // rows still pending; z of pend[0]; valid y of the row segment
-    size_t pidx = 0;         // element index of pend[0]
-    bool pok = false;
-#pragma unroll
-    for (int i = 0; i < kRZ; ++i)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) pend[i][r] = 0.f;
-
-    auto flush_rows = [&](int n) {
-        for (int j = 0; j < n && npend > 0; ++j) {
-            if (pok && pz < p.Z) store_row(pend[0][0], pend[0][1], pend[0][2], pend[0][3], p.pred, pidx, p.out_f64, pny, vec, p.dbg);
-#pragma unroll
-            for (int i = 0; i + 1 < kRZ; ++i)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) pend[i][r] = pend[i + 1][r];
-            --npend;
-            ++pz;
-            pidx += (size_t)p.X * p.Y;
-        }
-    };
 
     int k = 0;
     for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
         int b, z0, x0, y0;
         decode_tile(tile, g, b, z0, x0, y0);
-        const int buf = p.use_tma ? k % nstage : 0;
+        const int buf = p.use_tma ? (k & 1) : 0;
         const float* sx = sx0 + buf * halo_stride;
         if (p.use_tma) {
-            if (!(p.dbg & 4)) mbar_wait(&full[buf], (uint32_t)(k / nstage) & 1u);
+            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(k >> 1) & 1u);
         } else {
             __syncthreads();  // previous tile fully consumed
-            load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kFwdThreads);
+            load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
             __syncthreads();
         }
-        if (compute) {
-            float acc[kRZ][4];
-#pragma unroll
-            for (int i = 0; i < kRZ; ++i)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
 
-            // kz = nfull*C + REM with REM a template parameter: the hot loop holds exactly the bodies this kernel
-            // size needs (a runtime switch over all remainders inflated the code and cost ~7 %)
-            for (int dx = 0; dx < p.kx; ++dx) {
-                const float* sxrow = sx + (txi + dx) * g.WS + 4 * tyi;
-                const float* skrow = sk + dx * g.nchunks * CKP;
-                for (int ch = 0; ch < nfull; ++ch) fwd_chunk<KY, C>(acc, sxrow + (ch * C) * zstride, zstride, skrow + ch * CKP);
-                if constexpr (REM > 0) fwd_chunk<KY, REM>(acc, sxrow + (nfull * C) * zstride, zstride, skrow + nfull * CKP);
-                flush_rows(rows_per_dx);  // a slice of the previous tile's epilogue, hidden behind this tile's FFMAs
-            }
-            if (p.use_tma) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[buf]);  // this warp no longer reads the stage
-            }
-            flush_rows(kRZ);  // whatever is left of the previous tile (kx < 8/rows_per_dx cannot happen, but be safe)
-            // this tile becomes the pending one
+        float acc[kRZ][4];
 #pragma unroll
-            for (int i = 0; i < kRZ; ++i)
+        for (int i = 0; i < kRZ; ++i)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) pend[i][r] = acc[i][r];
-            const int gx = x0 + txi, gy = y0 + 4 * tyi;
-            pok = gx < p.X && gy < p.Y;
-            npend = kRZ;
-            pz = z0;
-            pny = p.Y - gy;
-            pidx = (((size_t)b * p.Z + z0) * p.X + (pok ? gx : 0)) * p.Y + (pok ? gy : 0);
+            for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+
+        // kz = nfull*C + REM with REM a template parameter: the hot loop holds exactly the bodies this
+        // kernel size needs (a runtime switch over all remainders inflated the code and cost ~7 %)
+        const int nfull = p.kz / C;
+        for (int dx = 0; dx < p.kx; ++dx) {
+            const float* sxrow = sx + (txi + dx) * g.WS + 4 * tyi;
+            const float* skrow = sk + dx * g.nchunks * CKP;
+            for (int ch = 0; ch < nfull; ++ch) fwd_chunk<KY, C>(acc, sxrow + (ch * C) * zstride, zstride, skrow + ch * CKP);
+            if constexpr (REM > 0) fwd_chunk<KY, REM>(acc, sxrow + (nfull * C) * zstride, zstride, skrow + nfull * CKP);
+        }
+
+        if (p.use_tma) {
+            __syncthreads();  // every thread is done reading this buffer -> refill it with tile k+2
+            if (tid == 0 && tile + 2 * G < g.ntiles && !(p.dbg & 4)) {
+                fence_proxy_async();
+                issue(tile + 2 * G, buf);
+            }
+        }
+
+        // epilogue: relu(tanh(s)) and store in the caller's dtype (overlaps the TMA just issued)
+        const int gx = x0 + txi, gy = y0 + 4 * tyi;
+        if (gx < p.X && gy < p.Y) {
+#pragma unroll
+            for (int zo = 0; zo < kRZ; ++zo) {
+                const int gz = z0 + zo;
+                if (gz < p.Z)
+                    store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy,
+                              p.out_f64, p.Y - gy, vec, p.dbg);
+            }
         }
     }
-    if (compute) flush_rows(kRZ);
 }
 
 template <int KY, int TYT, int REM>
@@ -222,23 +181,21 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
         const char* e = getenv("SN_FWD_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
-    const TileGeo g = make_geo<KY, TYT, kFwdMicro>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
     const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
     CUtensorMap tmap;
     p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
-    p.nstage = 2;
-    size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 64;
-    if (!p.use_tma || smem > 227 * 1024) {  // huge halo or no TMA: single stage
-        p.nstage = 1;
-        smem = (size_t)(halo_stride + tap_floats) * 4 + 64;
-    }
+    size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
+    if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
+    if (!p.use_tma) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
     if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     auto kern = stencil_fwd_kernel<KY, TYT, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    const int grid = max(1, min(g.ntiles, kNumSMs));
-    kern<<<grid, kFwdThreads, smem, stream>>>(p, tmap);
+    const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
+    const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
+    kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
