@@ -312,46 +312,75 @@ def main():
     eager_value = B_PER_GPU * world * 10 / (time.perf_counter() - t0)
 
     # ------------------------------------------------ e2e: host buffers, copies inside the timed region
-    xh = [torch.empty(pool[0][0].shape, dtype=io_dtype).pin_memory() for _ in range(2)]
-    for h in xh:
-        h.copy_(pool[0][0])
     n_e2e = max(3, min(args.steps, 20))
     gh = torch.zeros(len(trainable), dtype=torch.float32).pin_memory()
-    if args.eager:
-        xd = torch.empty_like(pool[0][0])
 
-        def e2e_step(i):
-            xd.copy_(xh[i % 2], non_blocking=True)               # H2D of this step's input grids
-            for p in trainable:
-                p.grad = None
-            pred = model(xd)
-            pred.backward(pool[i % n_sets][1])
-            if post:
-                post()
-            gh.copy_(torch.stack([p.grad for p in trainable]))    # D2H read of the step's result (synchronous)
-    else:
-        # the same step captured with its copies: H2D(x from pinned host) -> fwd -> bwd -> [all-reduce] -> D2H(grads)
-        e2e_graphs = [GraphedStep(model, torch.empty_like(pool[0][0]), dpred=pool[j][1], x_host=xh[j], grads_host=gh,
-                                  post_backward=post) for j in range(2)]
+    def e2e_measure(xh, dps):
+        """xh: two pinned host batches; dps: two device upstream gradients (dtype of the module's output).
+        Every step: H2D of that step's x (copy stream, double-buffered, overlapping the previous step's kernels) ->
+        fwd + bwd [+ all-reduce] + D2H of the gradients -> the host waits for the gradients."""
+        xd2 = [torch.empty(xh[0].shape, dtype=xh[0].dtype, device=device) for _ in range(2)]
+        gh2 = [torch.zeros(len(trainable), dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=device)
+        main_stream = torch.cuda.current_stream(device)
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        for e in ev_done:
+            e.record(main_stream)
+        if args.eager:
+            steps_ = None
+        else:
+            steps_ = [GraphedStep(model, xd2[j], dpred=dps[j], grads_host=gh2[j], post_backward=post) for j in range(2)]
+        state = {"next": 0}
 
-        def e2e_step(i):
-            e2e_graphs[i % 2].replay()
-            torch.cuda.current_stream().synchronize()             # the host reads the gradients every step
+        def prefetch(i):
+            j = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done[j])          # the step that last used this buffer has finished
+                xd2[j].copy_(xh[j], non_blocking=True)      # H2D of step i's input grids
+                ev_copied[j].record(copy_stream)
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = B_PER_GPU * world * n_e2e / float(e2e_s)
-    h2d = xh[0].numel() * xh[0].element_size()
+        def one(i):
+            j = i % 2
+            while state["next"] <= i + 1:                    # this step's input, and the next one's while we compute
+                prefetch(state["next"])
+                state["next"] += 1
+            main_stream.wait_event(ev_copied[j])
+            if steps_ is not None:
+                steps_[j].replay()
+            else:
+                for p in trainable:
+                    p.grad = None
+                pred = model(xd2[j])
+                pred.backward(dps[j])
+                if post:
+                    post()
+                gh2[j].copy_(torch.stack([p.grad for p in trainable]), non_blocking=True)
+            ev_done[j].record(main_stream)
+            ev_done[j].synchronize()                         # the host reads this step's gradients
+            gh.copy_(gh2[j])
+
+        for i in range(3):
+            one(i)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(3, 3 + n_e2e):
+            one(i)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return B_PER_GPU * world * n_e2e / float(dt), xh[0].numel() * xh[0].element_size()
+
+    xh = [torch.empty(pool[0][0].shape, dtype=io_dtype).pin_memory() for _ in range(2)]
+    for j, h in enumerate(xh):
+        h.copy_(pool[j][0])
+    e2e_value, h2d = e2e_measure(xh, [pool[0][1], pool[1][1]])
     d2h = gh.numel() * gh.element_size()
+    # the same step fed with byte occupancy grids (what ToFullDense produces; module extension): 8x fewer PCIe bytes
+    xh8 = [h.to(torch.uint8).pin_memory() for h in xh]
+    e2e_u8_value, h2d_u8 = e2e_measure(xh8, [pool[0][1].float(), pool[1][1].float()])
 
     # ------------------------------------------------ roofline of the two stencil kernels, timed alone with CUDA events
     roof = None
@@ -423,7 +452,9 @@ def main():
                        "eager_module_value": eager_value,
                        "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                    "note": "x from pinned host memory each step; dL/dpred resident on the device (config 2(i)); gradients read back"},
+                    "uint8_occupancy_input": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8},
+                    "note": "x (module-boundary dtype) from pinned host memory every step, double-buffered on a copy stream; "
+                            "dL/dpred resident on the device (config 2(i)); gradients copied back and read by the host every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "voxelize": vox,
         }
         print(json.dumps(line))

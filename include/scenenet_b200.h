@@ -154,6 +154,8 @@ int sn_scenenet_tapgrad(const float* x, const float* g0, int B, int Z, int X, in
  * ====================================================================================== */
 /* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */
 int sn_cast_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
+/* uint8 / bool occupancy grids (what ToFullDense produces, one byte per voxel) -> float32; 16-byte aligned */
+int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n, void* stream);
 /* prob_to_label (utils/voxelization.py:304-323) / SCENE_Net_Class.forward (SCENE_Net.py:465-466):
  * out = (p >= tau) as 0/1, same dtype as p. */
 int sn_threshold(const void* p, int dtype, double tau, int64_t n, void* out, void* stream);

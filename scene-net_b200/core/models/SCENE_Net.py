@@ -30,6 +30,7 @@ class _ObserverFunction(torch.autograd.Function):
     def forward(ctx, x, spec, write_last, grad_scale, *params):
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         x32 = ops.cast_f32(x.detach())
+        # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
         ctx.spec = spec
         ctx.grad_scale = grad_scale

@@ -15,6 +15,22 @@ __global__ void __launch_bounds__(256) cast_f64_f32_kernel(const double* __restr
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = (float)in[n - 1];
 }
 
+// uint8 / bool occupancy -> float32, 16 voxels per thread per step (one 16-byte load, four 16-byte stores)
+__global__ void __launch_bounds__(256) cast_u8_f32_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long n16 = n >> 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = make_float4((float)(w[k] & 0xffu), (float)((w[k] >> 8) & 0xffu), (float)((w[k] >> 16) & 0xffu), (float)(w[k] >> 24));
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) out[i] = (float)in[i];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) threshold_kernel(const T* __restrict__ p, T tau, long long n, T* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -55,6 +71,15 @@ extern "C" int sn_cast_f64_to_f32(const double* in, float* out, int64_t n, void*
     if (n == 0) return SN_OK;
     if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return SN_ERR_ALIGN;
     sn::cast_f64_f32_kernel<<<sn::grid_for(n / 2 + 1, 256 * 4), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n, void* stream) {
+    if (!in || !out || n < 0) return SN_ERR_BAD_ARG;
+    if (n == 0) return SN_OK;
+    if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return SN_ERR_ALIGN;
+    sn::cast_u8_f32_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, (cudaStream_t)stream>>>(in, out, n);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -16,7 +16,6 @@
 namespace sn {
 
 constexpr int kSynthThreads = 256;
-constexpr int kMaxPerThread = SN_MAX_TAPS / kSynthThreads;  // 16
 constexpr float kEpsV2 = 1e-8f;
 constexpr float kPiF = 3.14159265358979323846f;
 
@@ -119,12 +118,18 @@ __device__ __forceinline__ float raw_value(int kind, const OpParams& o, int t, i
     return exp_rn((u * u) * c);
 }
 
-__device__ __forceinline__ double block_sum(double v, double* red) {
+// The CTA is split into up to kSynthGroups groups of kSynthThreads threads; each group synthesises (or
+// differentiates) its own operators concurrently and synchronises on its own named barrier.
+constexpr int kSynthGroups = 4;
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kSynthThreads) : "memory");
+}
+__device__ __forceinline__ double group_sum(double v, double* red, int group) {
     v = warp_sum(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
+    const int w = (threadIdx.x % kSynthThreads) >> 5, l = threadIdx.x & 31;
+    group_sync(group);
     if (l == 0) red[w] = v;
-    __syncthreads();
+    group_sync(group);
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < kSynthThreads / 32; ++i) s += red[i];
@@ -140,31 +145,31 @@ __device__ float lambda_eff_of(const SynthArgs& a, int g) {
 }
 
 // =====================================================================================
-__global__ void __launch_bounds__(kSynthThreads, 1)
-synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* __restrict__ K, float* __restrict__ lambda_eff,
+__global__ void __launch_bounds__(kSynthThreads * kSynthGroups, 1)
+synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restrict__ lambda_eff,
                  float* __restrict__ Kstar, float* __restrict__ snapshot, int write_last) {
-    __shared__ float s_raw[SN_MAX_TAPS];
-    __shared__ float s_off[64];  // per-slice mean (plane kinds) or [0] = volume offset
-    __shared__ double s_red[kSynthThreads / 32];
+    extern __shared__ float s_raw_all[];  // [groups][Tp]
+    __shared__ float s_off_all[kSynthGroups][64];  // per-slice mean (plane kinds) or [0] = volume offset
+    __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
     __shared__ float s_lam[SN_MAX_GENEOS];
 
-    const int kz = a.d.kz, kx = a.d.kx, ky = a.d.ky, P = kx * ky, T = kz * P;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kz = a.d.kz, kx = a.d.kx, ky = a.d.ky, P = kx * ky, T = kz * P, Tp = (T + 31) & ~31;
+    const int tid = threadIdx.x, group = tid / kSynthThreads, lt = tid % kSynthThreads, warp = lt >> 5, lane = tid & 31;
+    const int ngroups = blockDim.x / kSynthThreads;
     const bool observer = a.d.lambda_index[0] >= 0;
+    float* s_raw = s_raw_all + group * Tp;
+    float* s_off = s_off_all[group];
+    double* s_red = s_red_all[group];
 
     if (tid < a.d.n_geneos) s_lam[tid] = lambda_eff_of(a, tid);
     if (snapshot && tid < a.d.n_param_ptrs) snapshot[tid] = *a.p[tid];
     __syncthreads();
 
-    double kacc[kMaxPerThread];
-#pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) kacc[i] = 0.0;
-
-    for (int g = 0; g < a.d.n_geneos; ++g) {
+    for (int g = group; g < a.d.n_geneos; g += ngroups) {
         const int kind = a.d.kind[g];
         const OpParams o = load_op(a, g);
-        for (int t = tid; t < T; t += kSynthThreads) s_raw[t] = raw_value(kind, o, t, kz, kx, ky);
-        __syncthreads();
+        for (int t = lt; t < T; t += kSynthThreads) s_raw[t] = raw_value(kind, o, t, kz, kx, ky);
+        group_sync(group);
         if (is_plane_kind(kind)) {
             // zero-sum per z slice: f - sum(f)/(kx*ky)   (cylinder.py:81-82, arrow.py:167-168)
             for (int z = warp; z < kz; z += kSynthThreads / 32) {
@@ -173,43 +178,39 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* __restrict__ K, flo
                 s = warp_sum(s);
                 if (lane == 0) s_off[z] = (float)s / (float)P;
             }
-            __syncthreads();
+            group_sync(group);
         } else {
             double s = 0.0;
-            for (int t = tid; t < T; t += kSynthThreads) s += (double)s_raw[t];
-            s = block_sum(s, s_red);
-            if (tid == 0) {
+            for (int t = lt; t < T; t += kSynthThreads) s += (double)s_raw[t];
+            s = group_sum(s, s_red, group);
+            if (lt == 0) {
                 if (kind == SN_KIND_NEGSPHERE_V2)
                     s_off[0] = ((float)s + o.neg_factor) / (float)T;  // sum_negfactor (neg_sphere.py:181-182)
                 else
                     s_off[0] = (float)s / (float)T;  // sum_zero (neg_sphere.py:126-127)
             }
-            __syncthreads();
+            group_sync(group);
         }
-        const float lam = s_lam[g];
-#pragma unroll
-        for (int i = 0; i < kMaxPerThread; ++i) {
-            const int t = tid + i * kSynthThreads;
-            if (t < T) {
-                float k;
-                if (is_plane_kind(kind))
-                    k = s_raw[t] - s_off[t / P];
-                else if (kind == SN_KIND_NEGSPHERE_V2)
-                    k = s_raw[t] - s_off[0];
-                else
-                    k = (s_raw[t] - s_off[0]) - o.neg_factor;  // neg_sphere.py:148
-                K[(size_t)g * T + t] = k;
-                kacc[i] += (double)lam * (double)k;
-            }
+        for (int t = lt; t < T; t += kSynthThreads) {
+            float k;
+            if (is_plane_kind(kind))
+                k = s_raw[t] - s_off[t / P];
+            else if (kind == SN_KIND_NEGSPHERE_V2)
+                k = s_raw[t] - s_off[0];
+            else
+                k = (s_raw[t] - s_off[0]) - o.neg_factor;  // neg_sphere.py:148
+            K[(size_t)g * T + t] = k;
         }
-        __syncthreads();
+        group_sync(group);
     }
     if (observer) {
+        __threadfence_block();
+        __syncthreads();  // every operator's kernel is in K now
         if (Kstar) {
-#pragma unroll
-            for (int i = 0; i < kMaxPerThread; ++i) {
-                const int t = tid + i * kSynthThreads;
-                if (t < T) Kstar[t] = (float)kacc[i];
+            for (int t = tid; t < T; t += blockDim.x) {
+                double acc = 0.0;  // Kstar = sum_g lambda_eff[g] * K_g, float64, fixed order
+                for (int g = 0; g < a.d.n_geneos; ++g) acc += (double)s_lam[g] * (double)K[(size_t)g * T + t];
+                Kstar[t] = (float)acc;
             }
         }
         if (lambda_eff && tid < a.d.n_geneos) lambda_eff[tid] = s_lam[tid];
@@ -223,19 +224,22 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* __restrict__ K, flo
 // plus dlambda_g = <K_g - K_last, W>.
 // =====================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(kSynthThreads, 1)
+__global__ void __launch_bounds__(kSynthThreads * kSynthGroups, 1)
 synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__ dK, const float* __restrict__ K,
                  const float* __restrict__ lambda_eff, const double* __restrict__ W, double scale,
                  float* __restrict__ dparams) {
-    __shared__ double s_mean[64];
-    __shared__ double s_red[kSynthThreads / 32];
+    __shared__ double s_mean_all[kSynthGroups][64];
+    __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
     const int kz = a.d.kz, kx = a.d.kx, ky = a.d.ky, P = kx * ky, T = kz * P;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = threadIdx.x / kSynthThreads, ngroups = blockDim.x / kSynthThreads;
+    const int tid = threadIdx.x % kSynthThreads, warp = tid >> 5, lane = tid & 31;  // tid: within the group
+    double* s_mean = s_mean_all[group];
+    double* s_red = s_red_all[group];
 
-    for (int i = tid; i < a.d.n_param_ptrs; i += kSynthThreads) dparams[i] = 0.f;
+    for (int i = threadIdx.x; i < a.d.n_param_ptrs; i += blockDim.x) dparams[i] = 0.f;
     __syncthreads();
 
-    for (int g = 0; g < a.d.n_geneos; ++g) {
+    for (int g = group; g < a.d.n_geneos; g += ngroups) {
         const int kind = a.d.kind[g];
         const OpParams o = load_op(a, g);
         const bool plane = is_plane_kind(kind);
@@ -251,11 +255,11 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
                 s = warp_sum(s);
                 if (lane == 0) s_mean[z] = s / (double)P;
             }
-            __syncthreads();
+            group_sync(group);
         } else {
             double s = 0.0;
             for (int t = tid; t < T; t += kSynthThreads) s += dk(t);
-            vol_mean = block_sum(s, s_red) / (double)T;
+            vol_mean = group_sum(s, s_red, group) / (double)T;
         }
 
         double acc[5] = {0, 0, 0, 0, 0};  // indexed like the operator's alphabetical parameter list
@@ -321,7 +325,7 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
         }
         const int np = n_params_of(kind);
         for (int k = 0; k < np; ++k) {
-            double s = block_sum(acc[k], s_red);
+            double s = group_sum(acc[k], s_red, group);
             if (kind == SN_KIND_NEGSPHERE_V2 && k == 0) s += -vol_mean;             // direct -nf/T term
             if (kind == SN_KIND_NEGSPHERE_V1 && k == 0) s += -vol_mean * (double)T;  // direct -nf term
             if (tid == 0) dparams[a.d.param_index[g] + k] = (float)(s * scale);
@@ -336,10 +340,10 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
                 if (last >= 0) kd -= (double)K[(size_t)last * T + t];
                 s += kd * W[t];
             }
-            s = block_sum(s, s_red);
+            s = group_sum(s, s_red, group);
             if (tid == 0) dparams[a.d.lambda_index[g]] = (float)(s * scale);
         }
-        __syncthreads();
+        group_sync(group);
     }
 }
 
@@ -380,7 +384,14 @@ extern "C" int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const*
     if (!K) return SN_ERR_BAD_ARG;
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
-    sn::synth_fwd_kernel<<<1, sn::kSynthThreads, 0, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, param_snapshot, write_last_lambda);
+    const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
+    const int Tp = (desc->kz * desc->kx * desc->ky + 31) & ~31;
+    const size_t smem = (size_t)groups * Tp * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sn::synth_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return sn::cuda_rc(e);
+    }
+    sn::synth_fwd_kernel<<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, param_snapshot, write_last_lambda);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -392,7 +403,8 @@ extern "C" int sn_geneo_synth_bwd(const sn_model_desc* desc, const float* const*
     if (!dK || !dparams) return SN_ERR_BAD_ARG;
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
-    sn::synth_bwd_kernel<0><<<1, sn::kSynthThreads, 0, (cudaStream_t)stream>>>(a, dK, nullptr, nullptr, nullptr, 1.0, dparams);
+    const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
+    sn::synth_bwd_kernel<0><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, dK, nullptr, nullptr, nullptr, 1.0, dparams);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -405,7 +417,8 @@ extern "C" int sn_scenenet_param_grads(const sn_model_desc* desc, const float* c
     if (!K || !lambda_eff || !W || !dparams || desc->lambda_index[0] < 0) return SN_ERR_BAD_ARG;
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
-    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams);
+    const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
+    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

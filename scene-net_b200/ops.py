@@ -154,8 +154,17 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, "x")
     if x.dtype == torch.float32:
         return x.contiguous()
+    if x.dtype in (torch.uint8, torch.bool):  # occupancy grids as bytes (8x less PCIe/HBM traffic than float64)
+        x = x.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone()
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        if x.numel():
+            with torch.cuda.device(x.device):
+                check(lib.sn_cast_u8_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "sn_cast_u8_to_f32")
+        return out
     if x.dtype != torch.float64:
-        raise TypeError(f"voxel grids must be float32 or float64, got {x.dtype}")
+        raise TypeError(f"voxel grids must be float64, float32, uint8 or bool, got {x.dtype}")
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     if x.numel() == 0:

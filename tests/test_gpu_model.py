@@ -345,6 +345,17 @@ def test_empty_batch_and_errors():
         m(torch.zeros(1, 1, 8, 8, 8, dtype=torch.int32, device=DEV))
 
 
+def test_byte_occupancy_input_equals_float_input():
+    """uint8 / bool occupancy grids (extension) give exactly the float32 path's result."""
+    x, _ = mo.synthetic_grids(3, (24, 20, 36), seed=8, dtype=torch.float32)
+    x = x.to(DEV)
+    m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+    ref = m(x)
+    for dt in (torch.uint8, torch.bool):
+        out = m(x.to(dt))
+        assert out.dtype == torch.float32 and torch.equal(out, ref)
+
+
 def test_graphed_step_matches_eager():
     """CUDA-graph replay of the captured module step gives bit-identical predictions and gradients."""
     from scenenet_b200.graphs import GraphedStep
