@@ -27,13 +27,14 @@ class _ObserverFunction(torch.autograd.Function):
     """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
 
     @staticmethod
-    def forward(ctx, x, spec, write_last, grad_scale, *params):
+    def forward(ctx, x, spec, write_last, grad_scale, sync_group, *params):
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         x32 = ops.cast_f32(x.detach())
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
         ctx.spec = spec
         ctx.grad_scale = grad_scale
+        ctx.sync_group = sync_group
         ctx.save_for_backward(x32, pred, K, lam, snap)
         return pred
 
@@ -42,9 +43,14 @@ class _ObserverFunction(torch.autograd.Function):
         x32, pred, K, lam, snap = ctx.saved_tensors
         W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size)
         d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
+        if ctx.sync_group is not None:
+            # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
+            # no pack / unpack kernels; the parameter .grads are views into it
+            import torch.distributed as dist
+            dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
         unused = ctx.spec.unused
-        grads = [d[i] if (ctx.needs_input_grad[i + 4] and i not in unused) else None for i in range(d.numel())]
-        return (None, None, None, None, *grads)
+        grads = [d[i] if (ctx.needs_input_grad[i + 5] and i not in unused) else None for i in range(d.numel())]
+        return (None, None, None, None, None, *grads)
 
 
 def _apex_int(layer) -> int:
@@ -140,6 +146,9 @@ class _SceneNetBase(nn.Module):
         self.lambdas_dict = nn.ParameterDict(lambdas_dict)
         #: multiply every parameter gradient by this (1/world_size gives DDP-mean semantics without a second pass)
         self.grad_scale = 1.0
+        #: None = no collective (single GPU, or DDP/Lightning does it); True / a process group = all-reduce (SUM) the
+        #: flat gradient payload inside backward (use with grad_scale = 1/world for the DDP mean)
+        self.grad_sync_group = None
         if plot:
             print(f"Total Number of train params = {self.get_num_total_params()}")
 
@@ -206,7 +215,7 @@ class _SceneNetBase(nn.Module):
         if x.device != params[0].device:
             raise RuntimeError(f"input on {x.device} but model on {params[0].device}")
         # write_last=True reproduces the side effect of SCENE_Net.py:333 (last lambda <- 1 - sum(others)), in place
-        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), *params)
+        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, *params)
 
 
 class SCENE_Net(_SceneNetBase):

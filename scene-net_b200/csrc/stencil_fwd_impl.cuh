@@ -80,14 +80,14 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
 // is being computed.  (The first version launched one CTA per tile: all CTAs of a wave waited for
 // their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
 template <int KY, int TYT, int REM>
-__global__ void __launch_bounds__(kStencilThreads, 2)
+__global__ void __launch_bounds__(kStencilThreads, 4)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
-    const int nbuf = p.use_tma ? 2 : 1;
+    const int nbuf = (p.use_tma && !(p.dbg & 16)) ? 2 : 1;  // dbg 16: single stage, more CTAs per SM (experiment)
     float* sx0 = reinterpret_cast<float*>(smem_raw);
     float* sk = sx0 + nbuf * halo_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
@@ -106,7 +106,7 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
         mbar_init(&bar[1], 1);
         fence_barrier_init();
         if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
-        if ((int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
+        if (nbuf == 2 && (int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
     }
     // taps -> shared once per CTA, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
     for (int i = tid; i < p.kx * g.nchunks * CKP; i += kStencilThreads) sk[i] = 0.f;
@@ -126,10 +126,10 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
     for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
         int b, z0, x0, y0;
         decode_tile(tile, g, b, z0, x0, y0);
-        const int buf = p.use_tma ? (k & 1) : 0;
+        const int buf = nbuf == 2 ? (k & 1) : 0;
         const float* sx = sx0 + buf * halo_stride;
         if (p.use_tma) {
-            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(k >> 1) & 1u);
+            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(nbuf == 2 ? (k >> 1) : k) & 1u);
         } else {
             __syncthreads();  // previous tile fully consumed
             load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
@@ -154,9 +154,9 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
 
         if (p.use_tma) {
             __syncthreads();  // every thread is done reading this buffer -> refill it with tile k+2
-            if (tid == 0 && tile + 2 * G < g.ntiles && !(p.dbg & 4)) {
+            if (tid == 0 && tile + nbuf * G < g.ntiles && !(p.dbg & 4)) {
                 fence_proxy_async();
-                issue(tile + 2 * G, buf);
+                issue(tile + nbuf * G, buf);
             }
         }
 
@@ -188,12 +188,12 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
     p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
     size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
     if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
-    if (!p.use_tma) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
+    if (!p.use_tma || (p.dbg & 16)) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
     if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     auto kern = stencil_fwd_kernel<KY, TYT, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
+    const int per_sm = max(1, min((p.dbg & 16) ? 4 : 2, (int)((227 * 1024) / (smem + 1024))));
     const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
     kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
     SN_LAUNCH_CHECK();
