@@ -170,16 +170,17 @@ static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
     constexpr int MICRO = kStencilThreads;  // TX * TYT
     BwdPlan pl;
     pl.ncombos = kx * g.nchunks;
-    const int max_warps = kBwdMaxThreads / 32;
+    static const int exp_mode = getenv("SN_BWD_PLAN") ? atoi(getenv("SN_BWD_PLAN")) : 0;  // experiments: 1 = 2 CTAs x 10 warps, single stage
+    const int max_warps = exp_mode == 1 ? 10 : kBwdMaxThreads / 32;
     pl.grid_y = ceil_div(pl.ncombos, max_warps);
     pl.combos_per_cta = ceil_div(pl.ncombos, pl.grid_y);
     pl.Q = 1;
     while (pl.Q * 2 <= MICRO / 32 && pl.combos_per_cta * pl.Q * 2 <= max_warps) pl.Q *= 2;
     pl.threads = pl.combos_per_cta * pl.Q * 32;
     const size_t stage = (size_t)(((g.HZ * g.HX * g.WS + 31) & ~31) + kRZ * g.TX * g.TY) * 4;
-    pl.nstage = (2 * stage + 64 <= 227 * 1024) ? 2 : 1;
+    pl.nstage = (exp_mode != 1 && 2 * stage + 64 <= 227 * 1024) ? 2 : 1;
     pl.smem = pl.nstage * stage + 64;
-    int gx = kNumSMs / pl.grid_y;
+    int gx = (exp_mode == 1 ? 2 * kNumSMs : kNumSMs) / pl.grid_y;
     gx = max(1, min(gx, g.ntiles));
     pl.grid_x = gx;
     pl.TP = (kz * kx * KY + 31) & ~31;

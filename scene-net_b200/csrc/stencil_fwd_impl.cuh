@@ -75,9 +75,9 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
     }
 }
 
-// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... with a
-// two-stage TMA pipeline: the halo of tile k+2 is in flight while tile k+1 waits ready and tile k
-// is being computed.  (The first version launched one CTA per tile: all CTAs of a wave waited for
+// Persistent CTAs (4 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a CTA's halo
+// load (one TMA box) is covered by the other CTAs of the SM (optionally a two-stage pipeline with 2 CTAs
+// per SM: tile k+2 in flight while tile k is being computed).  (The first version launched one CTA per tile: all CTAs of a wave waited for
 // their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
 template <int KY, int TYT, int REM>
 __global__ void __launch_bounds__(kStencilThreads, 4)
@@ -87,7 +87,9 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
-    const int nbuf = (p.use_tma && !(p.dbg & 16)) ? 2 : 1;  // dbg 16: single stage, more CTAs per SM (experiment)
+    // single stage + 4 CTAs per SM measured 4.5 % faster than two stages + 2 CTAs per SM (the other CTAs cover
+    // a CTA's halo wait and its tanhf epilogue); dbg 16 selects the two-stage variant
+    const int nbuf = (p.use_tma && (p.dbg & 16)) ? 2 : 1;
     float* sx0 = reinterpret_cast<float*>(smem_raw);
     float* sk = sx0 + nbuf * halo_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
@@ -188,12 +190,12 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
     p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
     size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
     if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
-    if (!p.use_tma || (p.dbg & 16)) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
+    if (!p.use_tma || !(p.dbg & 16)) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
     if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     auto kern = stencil_fwd_kernel<KY, TYT, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    const int per_sm = max(1, min((p.dbg & 16) ? 4 : 2, (int)((227 * 1024) / (smem + 1024))));
+    const int per_sm = max(1, min((p.dbg & 16) ? 2 : 4, (int)((227 * 1024) / (smem + 1024))));
     const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
     kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
     SN_LAUNCH_CHECK();
