@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 1
+#define SN_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define SN_OK 0
@@ -41,6 +41,7 @@ extern "C" {
 /* ---- dtypes of grid tensors crossing the boundary ------------------------------------ */
 #define SN_F32 0
 #define SN_F64 1
+#define SN_U8 2 /* occupancy bytes (uint8 / bool); accepted by sn_grid_prepare only */
 
 /* ---- GENEO operator kinds (core/models/geneos/) -------------------------------------- */
 #define SN_KIND_CYLINDER_V1 0 /* cylinder.py:30-140   cylinder_kernel   params: radius, sigma                */
@@ -132,26 +133,43 @@ int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z, int X, int
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
  *   G0 = dpred * (1 - pred^2) * [pred > 0];   W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t]
  *   x [B,1,Z,X,Y] float32, pred / dpred in pred_dtype / dpred_dtype, W [T] float64 out.
+ *   nnz: DEVICE pointer to the number of non-zero voxels of x as written by sn_grid_prepare, or NULL.
+ *        Voxel grids of point clouds are ~98 % empty: when nnz is given, an occupancy-driven
+ *        kernel (cost proportional to the occupied voxels) and the dense stencil are both enqueued and the
+ *        count selects ON THE DEVICE which of them does the work (sparse up to 10 % occupancy; no host
+ *        synchronisation).  With NULL the dense stencil always runs.  Same W either way, up to float32
+ *        summation order (the occupancy-driven kernel only skips terms that are exactly zero).
  *   ws: workspace of at least sn_scenenet_bwd_workspace_bytes(...) bytes, 16-byte aligned.
  * Deterministic: fixed partition, fixed-order float64 reduction, no floating-point atomics. */
 int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
-int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
-                    int B, int Z, int X, int Y, int kz, int kx, int ky,
+int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, const void* pred, int pred_dtype,
+                    const void* dpred, int dpred_dtype, int B, int Z, int X, int Y, int kz, int kx, int ky,
                     double* W, void* ws, int64_t ws_bytes, void* stream);
 
 /* The two passes of sn_scenenet_bwd, callable on their own (measurement, fused criterions that
  * produce G0 themselves):  G0 [n] float32 = dpred * (1 - pred^2) * [pred > 0] evaluated in float64 and
  * rounded once;  tap gradient W[t] = sum G0 * xpad from a precomputed G0.
- * sn_scenenet_bwd's workspace = G0 (n*4 bytes rounded up to 256) followed by the tap-gradient workspace. */
+ * sn_scenenet_bwd's workspace = G0 (n*4 bytes rounded up to 256) followed by the tap-gradient workspace.
+ * mode: SN_TAPGRAD_AUTO (device-side selection from nnz; dense when nnz is NULL), SN_TAPGRAD_DENSE,
+ *       SN_TAPGRAD_SPARSE (forced, nnz ignored; measurement and tests). */
+#define SN_TAPGRAD_AUTO 0
+#define SN_TAPGRAD_DENSE 1
+#define SN_TAPGRAD_SPARSE 2
 int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpred, int dpred_dtype, int64_t n, float* g0,
                    void* stream);
 int64_t sn_scenenet_tapgrad_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
-int sn_scenenet_tapgrad(const float* x, const float* g0, int B, int Z, int X, int Y, int kz, int kx, int ky,
+int sn_scenenet_tapgrad(const float* x, const float* g0, const unsigned long long* nnz, int mode,
+                        int B, int Z, int X, int Y, int kz, int kx, int ky,
                         double* W, void* ws, int64_t ws_bytes, void* stream);
 
 /* ======================================================================================
  * elementwise helpers
  * ====================================================================================== */
+/* Grid preparation, one HBM pass: x (SN_F64 as handed over by the reference's ToTensor, torch_transforms.py:13;
+ * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
+ * nothing is copied) and *nnz = number of non-zero voxels (device, 8-byte aligned; zeroed by the call).
+ * x and x32 16-byte aligned. */
+int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream);
 /* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */
 int sn_cast_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
 /* uint8 / bool occupancy grids (what ToFullDense produces, one byte per voxel) -> float32; 16-byte aligned */

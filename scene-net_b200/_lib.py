@@ -12,11 +12,12 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCENENET_B200_LIB", os.path.join(PKG, "libscenenet_b200.so"))  # override: experiments only
 
-SN_F32, SN_F64 = 0, 1
+SN_F32, SN_F64, SN_U8 = 0, 1, 2
+SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE = 0, 1, 2
 SN_MAX_GENEOS = 16
 SN_MAX_PARAM_PTRS = 96
 SN_MAX_TAPS = 4096
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 KIND = {
     "cylinder_kernel": 0, "cylinderv2": 1, "cone_kernel": 2, "arrow": 3, "neg_sphere_kernel": 4, "negSpherev2": 5,
@@ -50,10 +51,11 @@ SIGNATURES = {
     "sn_scenenet_param_grads": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _vp]),
     "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
-    "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sn_scenenet_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_scenenet_g0": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_scenenet_tapgrad_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
-    "sn_scenenet_tapgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sn_scenenet_tapgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sn_grid_prepare": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),

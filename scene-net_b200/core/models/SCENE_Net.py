@@ -29,19 +29,19 @@ class _ObserverFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, spec, write_last, grad_scale, sync_group, *params):
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
-        x32 = ops.cast_f32(x.detach())
+        x32, nnz = ops.prepare(x.detach())
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
         ctx.spec = spec
         ctx.grad_scale = grad_scale
         ctx.sync_group = sync_group
-        ctx.save_for_backward(x32, pred, K, lam, snap)
+        ctx.save_for_backward(x32, pred, K, lam, snap, nnz)
         return pred
 
     @staticmethod
     def backward(ctx, dpred):
-        x32, pred, K, lam, snap = ctx.saved_tensors
-        W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size)
+        x32, pred, K, lam, snap, nnz = ctx.saved_tensors
+        W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size, nnz)
         d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
         if ctx.sync_group is not None:
             # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,

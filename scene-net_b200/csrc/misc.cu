@@ -31,6 +31,78 @@ __global__ void __launch_bounds__(256) cast_u8_f32_kernel(const unsigned char* _
         for (long long i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) out[i] = (float)in[i];
 }
 
+
+// ---- sn_grid_prepare: cast to float32 + count the non-zero voxels (the count selects the occupancy-driven
+// kernels on the device).  Integer atomics only: the count is exact and order-independent.
+// (one atomic per CTA: thousands of same-address atomics at the end of the kernel were a visible serial tail)
+__device__ __forceinline__ void add_count(unsigned cnt, unsigned long long* nnz) {
+    __shared__ unsigned s_cnt[8];
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_cnt[i];
+        if (t) atomicAdd(nnz, (unsigned long long)t);
+    }
+}
+
+__global__ void __launch_bounds__(256) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
+                                                          unsigned long long* nnz) {
+    const long long n2 = n >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 v = reinterpret_cast<const double2*>(in)[i];
+        const float2 o = make_float2((float)v.x, (float)v.y);
+        reinterpret_cast<float2*>(out)[i] = o;
+        cnt += (o.x != 0.f) + (o.y != 0.f);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        out[n - 1] = (float)in[n - 1];
+        cnt += out[n - 1] != 0.f;
+    }
+    add_count(cnt, nnz);
+}
+
+__global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n,
+                                                         unsigned long long* nnz) {
+    const long long n16 = n >> 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned b0 = w[k] & 0xffu, b1 = (w[k] >> 8) & 0xffu, b2 = (w[k] >> 16) & 0xffu, b3 = w[k] >> 24;
+            o[k] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+            cnt += (b0 != 0) + (b1 != 0) + (b2 != 0) + (b3 != 0);
+        }
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) {
+            out[i] = (float)in[i];
+            cnt += in[i] != 0;
+        }
+    add_count(cnt, nnz);
+}
+
+__global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict__ in, long long n, unsigned long long* nnz) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(in)[i];
+        cnt += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) cnt += in[i] != 0.f;
+    add_count(cnt, nnz);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) threshold_kernel(const T* __restrict__ p, T tau, long long n, T* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -80,6 +152,27 @@ extern "C" int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n,
     if (n == 0) return SN_OK;
     if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return SN_ERR_ALIGN;
     sn::cast_u8_f32_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+
+extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream) {
+    if (!x || !nnz || n < 0) return SN_ERR_BAD_ARG;
+    if (dtype != SN_F32 && dtype != SN_F64 && dtype != SN_U8) return SN_ERR_BAD_ARG;
+    if (dtype != SN_F32 && !x32) return SN_ERR_BAD_ARG;
+    if (dtype == SN_F32 && x32 && (const void*)x32 != x) return SN_ERR_BAD_ARG;  // float32 grids are used in place
+    if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(nnz, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return sn::cuda_rc(e);
+    if (n == 0) return SN_OK;
+    if (dtype == SN_F64)
+        sn::prepare_f64_kernel<<<sn::grid_for(n / 2 + 1, 256 * 4), 256, 0, s>>>((const double*)x, x32, n, nnz);
+    else if (dtype == SN_U8)
+        sn::prepare_u8_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz);
+    else
+        sn::count_f32_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const float*)x, n, nnz);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -32,6 +32,11 @@ int64_t stencil_bwd_ws_ky13(int, int, int, int, int, int);
 int stencil_bwd_ky15(const BwdParams&, void*, int64_t, int*, int*, cudaStream_t);
 int64_t stencil_bwd_ws_ky15(int, int, int, int, int, int);
 int stencil_tapgrad_generic(const BwdParams& p, int ky, double* W, cudaStream_t stream);  // stencil_generic.cu
+// stencil_bwd_sparse.cu
+int64_t tapgrad_sparse_ws(int B, int Z, int X, int Y, int kz, int kx, int ky);
+int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long long* nnz, unsigned long long nnz_max,
+                          int B, int Z, int X, int Y, int kz, int kx, int ky, void* ws, int64_t ws_bytes, int* rows_out,
+                          cudaStream_t stream);
 
 // G0 = dpred * (1 - pred^2) * [pred > 0]: 4 voxels per thread, all loads issued before use
 template <typename TP, typename TD>
@@ -64,9 +69,14 @@ __global__ void __launch_bounds__(256) g0_kernel(const TP* __restrict__ pred, co
 }
 
 // W[t] = sum over partial rows in a fixed order (deterministic): block = 32 taps x 32 row groups
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partial, int rows, int TP, int T,
+// rows: the dense kernel's row count; rows_sparse: the occupancy-driven kernel's — the same device-side test as in
+// the two kernels tells which of them wrote the rows
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partial, int rows, int rows_sparse,
+                                                               const unsigned long long* __restrict__ nnz,
+                                                               unsigned long long nnz_max, int TP, int T,
                                                                double* __restrict__ W) {
     __shared__ double red[32][33];
+    if (nnz && *nnz <= nnz_max) rows = rows_sparse;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int t = blockIdx.x * 32 + tx;
     double s = 0.0;
@@ -111,7 +121,7 @@ static int launch_g0(const BwdParams& p, long long n, float* g0, cudaStream_t st
 
 }  // namespace sn
 
-static int64_t tapgrad_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
+static int64_t tapgrad_ws_dense(int B, int Z, int X, int Y, int kz, int kx, int ky) {
     switch (ky) {
         case 3: return sn::stencil_bwd_ws_ky3(B, Z, X, Y, kz, kx);
         case 5: return sn::stencil_bwd_ws_ky5(B, Z, X, Y, kz, kx);
@@ -123,6 +133,10 @@ static int64_t tapgrad_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
         case 15: return sn::stencil_bwd_ws_ky15(B, Z, X, Y, kz, kx);
         default: return 256;  // generic path needs no workspace
     }
+}
+static int64_t tapgrad_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    const int64_t a = tapgrad_ws_dense(B, Z, X, Y, kz, kx, ky), b = sn::tapgrad_sparse_ws(B, Z, X, Y, kz, kx, ky);
+    return a > b ? a : b;
 }
 static bool fast_ky(int ky) { return ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15; }
 
@@ -149,40 +163,79 @@ extern "C" int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpre
     return sn::launch_g0(p, n, g0, (cudaStream_t)stream);
 }
 
-extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, int B, int Z, int X, int Y, int kz, int kx, int ky,
+// occupancy (in percent of the voxels) up to which the occupancy-driven kernel is selected: measured break-even
+// at config 2 is ~11 % (dense 101 us flat; occupancy-driven 34 us + 5.5 us per percent, scratch/time_sparse.py)
+static unsigned long long sparse_nnz_max(long long nvox) {
+    static const int pct = getenv("SN_SPARSE_PCT") ? atoi(getenv("SN_SPARSE_PCT")) : 10;
+    return (unsigned long long)(nvox / 100 * pct);
+}
+
+extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsigned long long* nnz, int mode,
+                                   int B, int Z, int X, int Y, int kz, int kx, int ky,
                                    double* W, void* ws, int64_t ws_bytes, void* stream) {
     if (!x || !g0 || !W) return SN_ERR_BAD_ARG;
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    if (mode != SN_TAPGRAD_AUTO && mode != SN_TAPGRAD_DENSE && mode != SN_TAPGRAD_SPARSE) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
     if (ws && ((uintptr_t)ws & 15)) return SN_ERR_ALIGN;
+    if (nnz && ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
     sn::BwdParams p{};
     p.x = x; p.g0 = g0;
     p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!fast_ky(ky)) return sn::stencil_tapgrad_generic(p, ky, W, s);
-    if (!ws) return SN_ERR_WORKSPACE;
-    int rows = 0, TP = 0, rc;
-    switch (ky) {
-        case 3: rc = sn::stencil_bwd_ky3(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 5: rc = sn::stencil_bwd_ky5(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 6: rc = sn::stencil_bwd_ky6(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 7: rc = sn::stencil_bwd_ky7(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 9: rc = sn::stencil_bwd_ky9(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 11: rc = sn::stencil_bwd_ky11(p, ws, ws_bytes, &rows, &TP, s); break;
-        case 13: rc = sn::stencil_bwd_ky13(p, ws, ws_bytes, &rows, &TP, s); break;
-        default: rc = sn::stencil_bwd_ky15(p, ws, ws_bytes, &rows, &TP, s); break;
-    }
-    if (rc) return rc;
-    // fixed-order float64 reduction of the partial rows
     const int T = kz * kx * ky;
-    sn::reduce_partials_kernel<<<sn::ceil_div(T, 32), dim3(32, 32), 0, s>>>(reinterpret_cast<const double*>(ws), rows, TP, T, W);
+    const long long nvox = (long long)B * Z * X * Y;
+    const bool sparse_ok = ws && sn::tapgrad_sparse_ws(B, Z, X, Y, kz, kx, ky) > 0;
+    // which kernels are enqueued: forced modes run one of them unconditionally; AUTO with a count enqueues both and
+    // the device decides; widths the dense stencil is not instantiated for always take the occupancy-driven kernel
+    bool run_sparse, run_dense;
+    const unsigned long long* gate = nullptr;
+    if (mode == SN_TAPGRAD_SPARSE) {
+        if (!sparse_ok) return ws ? SN_ERR_UNSUPPORTED : SN_ERR_WORKSPACE;
+        run_sparse = true; run_dense = false;
+    } else if (mode == SN_TAPGRAD_DENSE || !sparse_ok) {
+        run_sparse = false; run_dense = true;
+    } else if (!fast_ky(ky)) {
+        run_sparse = true; run_dense = false;
+    } else if (nnz) {
+        run_sparse = run_dense = true; gate = nnz;
+    } else {
+        run_sparse = false; run_dense = true;
+    }
+    const unsigned long long nnz_max = sparse_nnz_max(nvox);
+    if (run_dense && !fast_ky(ky)) return sn::stencil_tapgrad_generic(p, ky, W, s);
+    if (!ws) return SN_ERR_WORKSPACE;
+    int rows = 0, rows_sparse = 0, TP = (T + 31) & ~31, rc = SN_OK;
+    if (run_sparse) {
+        rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, s);
+        if (rc) return rc;
+    }
+    if (run_dense) {
+        p.nnz = gate; p.nnz_max = nnz_max;
+        switch (ky) {
+            case 3: rc = sn::stencil_bwd_ky3(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 5: rc = sn::stencil_bwd_ky5(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 6: rc = sn::stencil_bwd_ky6(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 7: rc = sn::stencil_bwd_ky7(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 9: rc = sn::stencil_bwd_ky9(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 11: rc = sn::stencil_bwd_ky11(p, ws, ws_bytes, &rows, &TP, s); break;
+            case 13: rc = sn::stencil_bwd_ky13(p, ws, ws_bytes, &rows, &TP, s); break;
+            default: rc = sn::stencil_bwd_ky15(p, ws, ws_bytes, &rows, &TP, s); break;
+        }
+        if (rc) return rc;
+    } else {
+        rows = rows_sparse;  // ungated sparse run: the reduction reads its rows
+    }
+    // fixed-order float64 reduction of the partial rows
+    sn::reduce_partials_kernel<<<sn::ceil_div(T, 32), dim3(32, 32), 0, s>>>(reinterpret_cast<const double*>(ws), rows, rows_sparse,
+                                                                              gate, nnz_max, TP, T, W);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
 
-extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype, const void* dpred, int dpred_dtype,
-                               int B, int Z, int X, int Y, int kz, int kx, int ky, double* W, void* ws, int64_t ws_bytes,
-                               void* stream) {
+extern "C" int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, const void* pred, int pred_dtype,
+                               const void* dpred, int dpred_dtype, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                               double* W, void* ws, int64_t ws_bytes, void* stream) {
     if (!x || !pred || !dpred || !W || !ws) return SN_ERR_BAD_ARG;
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
     if ((uintptr_t)ws & 15) return SN_ERR_ALIGN;
@@ -191,5 +244,6 @@ extern "C" int sn_scenenet_bwd(const float* x, const void* pred, int pred_dtype,
     float* g0 = reinterpret_cast<float*>(ws);
     int rc = sn_scenenet_g0(pred, pred_dtype, dpred, dpred_dtype, (int64_t)B * Z * X * Y, g0, stream);
     if (rc) return rc;
-    return sn_scenenet_tapgrad(x, g0, B, Z, X, Y, kz, kx, ky, W, reinterpret_cast<char*>(ws) + gb, ws_bytes - gb, stream);
+    return sn_scenenet_tapgrad(x, g0, nnz, SN_TAPGRAD_AUTO, B, Z, X, Y, kz, kx, ky, W, reinterpret_cast<char*>(ws) + gb,
+                               ws_bytes - gb, stream);
 }

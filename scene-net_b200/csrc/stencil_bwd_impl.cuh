@@ -50,6 +50,7 @@ __device__ __forceinline__ void bwd_chunk(float (&acc)[Geo<KY>::C * KY], const f
 template <int KY, int TYT, int REM>
 __global__ void __launch_bounds__(kBwdMaxThreads, 1)
 stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap) {
+    if (p.nnz && *p.nnz <= p.nnz_max) return;  // sparse input: tapgrad_sparse_kernel does the work
     constexpr int C = Geo<KY>::C;
     constexpr int NACC = C * KY;
     constexpr int TY = TYT * 4, TX = kStencilThreads / TYT;

@@ -40,6 +40,11 @@ struct FwdParams {
     int B, Z, X, Y, kz, kx;
     int out_f64, use_tma;
     int dbg;  // debugging/profiling switches (SN_FWD_DBG): 1 = no stores, 2 = no tanh, 4 = no TMA
+    // z-split passes for kernels whose full halo would leave one 4-warp CTA per SM (13^3, 15^3): a pass applies
+    // the z-taps [dz0, dz0 + kz) of the full kernel (Kstar already points at tap dz0; plz = full left pad - dz0).
+    // pass_mode bit 0: add the partial sum the previous pass left in pred; bit 1: store the raw partial sum
+    // (no relu(tanh)) for the next pass.  Partial sums live in pred's own element slots (float -> double is exact).
+    int plz, pass_mode;
 };
 
 struct BwdParams {
@@ -53,6 +58,10 @@ struct BwdParams {
     int ncombos, combos_per_cta, TP;
     int Q, nstage;  // warps per tap group; TMA pipeline stages
     int dbg;        // profiling switch (SN_BWD_DBG): 4 = no TMA
+    // device-side selection between this dense stencil and the occupancy-driven kernel (stencil_bwd_sparse.cu):
+    // the dense kernel returns at once when nnz != NULL and *nnz <= nnz_max
+    const unsigned long long* nnz;
+    unsigned long long nnz_max;
 };
 
 // G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter
@@ -70,7 +79,7 @@ struct TileGeo {
 };
 
 template <int KY, int TYT>
-__host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, int kx) {
+__host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, int kx, int plz = -1000) {
     TileGeo g;
     g.TY = TYT * 4;
     g.TX = kStencilThreads / TYT;
@@ -82,7 +91,7 @@ __host__ __device__ inline TileGeo make_geo(int B, int Z, int X, int Y, int kz, 
     g.tiles_y = ceil_div(Y, g.TY);
     g.ntiles = B * g.tiles_z * g.tiles_x * g.tiles_y;
     g.nchunks = ceil_div(kz, Geo<KY>::C);
-    g.plz = pad_left(kz);
+    g.plz = plz == -1000 ? pad_left(kz) : plz;
     g.plx = pad_left(kx);
     g.ply = Geo<KY>::PLA;  // box start (aligned), not the conv pad
     return g;

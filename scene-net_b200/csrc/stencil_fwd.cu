@@ -28,7 +28,7 @@ extern "C" int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z,
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
     if (pred_dtype != SN_F32 && pred_dtype != SN_F64) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
-    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0};
+    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0};
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (ky) {

@@ -46,9 +46,22 @@ __device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __r
 // tanhf, not a float64 tanh: the double version cost ~27 % of the kernel's instructions and buys nothing
 // measurable (scratch/precision_probe.py: G0's float32 rounding in the backward dominates).
 static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, size_t idx, int out_f64, int ny,
-                                       bool vec, int dbg) {
+                                       bool vec, int dbg, int pass_mode) {
     float o[4] = {a0, a1, a2, a3};
-    if (!(dbg & 2)) {
+    if (pass_mode & 1) {  // z-split: add the previous passes' partial sum (stored in this row's own slots)
+        if (out_f64) {
+            const double* in = reinterpret_cast<const double*>(pred) + idx;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < ny) o[r] = (float)in[r] + o[r];
+        } else {
+            const float* in = reinterpret_cast<const float*>(pred) + idx;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < ny) o[r] = in[r] + o[r];
+        }
+    }
+    if (!(dbg & 2) && !(pass_mode & 2)) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) o[r] = o[r] > 0.f ? tanhf(o[r]) : 0.f;
     }
@@ -84,7 +97,7 @@ __global__ void __launch_bounds__(kStencilThreads, 4)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
     // single stage + 4 CTAs per SM measured 4.5 % faster than two stages + 2 CTAs per SM (the other CTAs cover
@@ -170,7 +183,7 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
                 const int gz = z0 + zo;
                 if (gz < p.Z)
                     store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy,
-                              p.out_f64, p.Y - gy, vec, p.dbg);
+                              p.out_f64, p.Y - gy, vec, p.dbg, p.pass_mode);
             }
         }
     }
@@ -183,7 +196,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
         const char* e = getenv("SN_FWD_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
-    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx);
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);
     const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
     const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
     CUtensorMap tmap;
@@ -215,9 +228,45 @@ struct FwdRemDispatch<KY, TYT, -1> {
     static int run(const FwdParams&, cudaStream_t) { return SN_ERR_UNSUPPORTED; }
 };
 
+// shared memory of one single-stage CTA for a pass with kz z-taps
+template <int KY, int TYT>
+static size_t fwd_pass_smem(const FwdParams& p, int kz) {
+    const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, kz, p.kx, 0);
+    const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
+    const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
+    return (size_t)(halo_stride + tap_floats) * 4 + 32;
+}
+
+template <int KY, int TYT>
+static int fwd_passes(const FwdParams& p0, cudaStream_t s) {
+    // z-split: as few passes as leave at least two CTAs (8 warps) per SM.  Measured on 128^3 grids before the
+    // split: 13^3 / 15^3 kernels ran one 4-warp CTA per SM at 26 % / 31 % of the FFMA peak, 9^3 / 11^3 (two
+    // CTAs) at 58 % / 69 % (profiles/r1_notes.md)
+    constexpr size_t kTwoPerSm = (227 * 1024 - 2048) / 2;
+    int npass = 1;
+    static const int forced = getenv("SN_FWD_PASSES") ? atoi(getenv("SN_FWD_PASSES")) : 0;
+    if (forced > 0)
+        npass = forced < p0.kz ? forced : p0.kz;
+    else
+        while (npass < p0.kz && fwd_pass_smem<KY, TYT>(p0, ceil_div(p0.kz, npass)) > kTwoPerSm) ++npass;
+    const int kzp = ceil_div(p0.kz, npass);
+    npass = ceil_div(p0.kz, kzp);
+    for (int i = 0; i < npass; ++i) {
+        FwdParams p = p0;
+        const int dz0 = i * kzp;
+        p.kz = (p0.kz - dz0) < kzp ? (p0.kz - dz0) : kzp;
+        p.Kstar = p0.Kstar + (size_t)dz0 * p0.kx * KY;
+        p.plz = pad_left(p0.kz) - dz0;
+        p.pass_mode = (i > 0 ? 1 : 0) | (i < npass - 1 ? 2 : 0);
+        const int rc = FwdRemDispatch<KY, TYT, Geo<KY>::C - 1>::run(p, s);
+        if (rc) return rc;
+    }
+    return SN_OK;
+}
+
 template <int KY>
 int stencil_fwd_ky(const FwdParams& p, cudaStream_t s) {
-    return p.Y > 32 ? FwdRemDispatch<KY, 16, Geo<KY>::C - 1>::run(p, s) : FwdRemDispatch<KY, 8, Geo<KY>::C - 1>::run(p, s);
+    return p.Y > 32 ? fwd_passes<KY, 16>(p, s) : fwd_passes<KY, 8>(p, s);
 }
 
 }  // namespace sn

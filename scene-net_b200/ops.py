@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import SN_F32, SN_F64, ModelDesc, check, lib
+from ._lib import SN_F32, SN_F64, SN_U8, ModelDesc, check, lib
 
 _DT = {torch.float32: SN_F32, torch.float64: SN_F64}
 
@@ -174,6 +174,29 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def prepare(x: torch.Tensor):
+    """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
+    (x itself for float32 input), nnz a 1-element int64 device tensor with the number of non-zero voxels: the
+    backward uses it ON THE DEVICE to pick the occupancy-driven tap-gradient kernel for sparse grids."""
+    _need_cuda(x, "x")
+    if x.dtype == torch.bool:
+        x = x.view(torch.uint8)
+    if x.dtype not in (torch.float64, torch.float32, torch.uint8):
+        raise TypeError(f"voxel grids must be float64, float32, uint8 or bool, got {x.dtype}")
+    x = x.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()
+    x32 = x if x.dtype == torch.float32 else torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return x32, torch.zeros(1, dtype=torch.int64, device=x.device)
+    nnz = torch.empty(1, dtype=torch.int64, device=x.device)
+    dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
+    with torch.cuda.device(x.device):
+        check(lib.sn_grid_prepare(x.data_ptr(), dt, x.numel(), None if x.dtype == torch.float32 else x32.data_ptr(),
+                                  nnz.data_ptr(), _stream()), "sn_grid_prepare")
+    return x32, nnz
+
+
 def _grid_dims(x: torch.Tensor):
     if x.dim() != 5 or x.shape[1] != 1:
         raise ValueError(f"expected a [B,1,Z,X,Y] voxel grid batch, got {tuple(x.shape)}")
@@ -206,8 +229,10 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, kernel_size) -> torch.Tensor:
-    """tap gradient W [kz,kx,ky] float64."""
+def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, kernel_size,
+                 nnz: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tap gradient W [kz,kx,ky] float64.  nnz (from `prepare`) enables the device-side choice of the
+    occupancy-driven kernel."""
     B, Z, X, Y = _grid_dims(x32)
     kz, kx, ky = (int(v) for v in kernel_size)
     _need_cuda(dpred, "dpred")
@@ -225,7 +250,7 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
     nbytes = int(lib.sn_scenenet_bwd_workspace_bytes(B, Z, X, Y, kz, kx, ky))
     ws = _workspace(nbytes, x32.device)
     with torch.cuda.device(x32.device):
-        check(lib.sn_scenenet_bwd(x32.data_ptr(), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
+        check(lib.sn_scenenet_bwd(x32.data_ptr(), _ptr(nnz), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
                                   B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
               "sn_scenenet_bwd")
     return W
@@ -240,14 +265,15 @@ def g0(pred: torch.Tensor, dpred: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def tapgrad(x32: torch.Tensor, g0_: torch.Tensor, kernel_size) -> torch.Tensor:
-    """W [kz,kx,ky] float64 from a precomputed G0 (pass 2 + 3 of the backward)."""
+def tapgrad(x32: torch.Tensor, g0_: torch.Tensor, kernel_size, nnz: Optional[torch.Tensor] = None, mode: int = 0) -> torch.Tensor:
+    """W [kz,kx,ky] float64 from a precomputed G0 (pass 2 + 3 of the backward).
+    mode: _lib.SN_TAPGRAD_AUTO / _DENSE / _SPARSE."""
     B, Z, X, Y = _grid_dims(x32)
     kz, kx, ky = (int(v) for v in kernel_size)
     W = torch.empty((kz, kx, ky), dtype=torch.float64, device=x32.device)
     ws = _workspace(int(lib.sn_scenenet_tapgrad_workspace_bytes(B, Z, X, Y, kz, kx, ky)), x32.device)
     with torch.cuda.device(x32.device):
-        check(lib.sn_scenenet_tapgrad(x32.data_ptr(), g0_.data_ptr(), B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(),
+        check(lib.sn_scenenet_tapgrad(x32.data_ptr(), g0_.data_ptr(), _ptr(nnz), int(mode), B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(),
                                       ws.numel(), _stream()), "sn_scenenet_tapgrad")
     return W
 
