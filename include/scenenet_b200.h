@@ -54,6 +54,8 @@ extern "C" {
 #define SN_MAX_GENEOS 16
 #define SN_MAX_PARAM_PTRS 96 /* 16 operators x 5 params + 16 lambdas */
 #define SN_MAX_TAPS 4096     /* up to 16^3 */
+#define SN_CRIT_MAX_BINS 12  /* histogram bins of the weighted-MSE scheme (the reference uses 10) */
+#define SN_CRIT_COEF (SN_CRIT_MAX_BINS + 4) /* doubles in the coefficient buffer of sn_criterion_fwd */
 
 /*
  * Host-side description of one observer (SceneNet / SCENE_Net instance,
@@ -161,6 +163,43 @@ int64_t sn_scenenet_tapgrad_workspace_bytes(int B, int Z, int X, int Y, int kz, 
 int sn_scenenet_tapgrad(const float* x, const float* g0, const unsigned long long* nnz, int mode,
                         int B, int Z, int X, int Y, int kz, int kx, int ky,
                         double* W, void* ws, int64_t ws_bytes, void* stream);
+
+/* ======================================================================================
+ * Fused criterion — replaces GENEO_Tversky_Loss.forward
+ * (core/criterions/geneo_loss.py:145-161) = WeightedMSE.forward (w_mse.py:114-151) +
+ * FocalTverskyLoss.forward (tversky_loss.py:81-95) + cvx_loss / positive_regularizer
+ * (geneo_loss.py:36-71), and their autograd backward.
+ *
+ *   loss = mean(mse_weight * w(y) * (y - p)^2) + (1 - Tv)^gamma,
+ *   w(y) = w_raw[bin(y)] / mean(w_raw[bin(y)]) in float32 (bin = first argmin_k |y - ranges[k]|),
+ *   Tv = (TP + s) / (TP + alpha FP + beta FN + s),  TP = sum p y, FP = sum (1-y) p, FN = sum y (1-p).
+ * ranges_host / w_raw_host: HOST arrays of nbins floats (the 10-entry table derived from the
+ * histogram pickle: w_raw[k] = max(1 - weight_alpha * dens_k, weight_epsilon), float32).
+ * pred / y: DEVICE, dtype SN_F32 or SN_F64 (both the same), 16-byte aligned.
+ * terms: bit 0 = weighted-MSE term, bit 1 = focal-Tversky term (WeightedMSE alone = 1, FocalTverskyLoss alone = 2).
+ * sn_criterion_fwd: one pass over (pred, y) + a one-warp finalisation; loss [1] and coef [SN_CRIT_COEF]
+ *   are DEVICE doubles; coef holds the closed-form backward's scalars (and, at [MAX+2], [MAX+3], the two terms).
+ * sn_criterion_bwd: one elementwise pass; grad_out = DEVICE scalar of the tensors' dtype (NULL = 1):
+ *   out_g0 == 0: out = dL/dpred [n] in the tensors' dtype;
+ *   out_g0 != 0: out = G0 [n] float32 = dL/dpred * (1 - pred^2) * [pred > 0], ready for sn_scenenet_tapgrad.
+ * Deterministic (no floating-point atomics).
+ * ====================================================================================== */
+int64_t sn_criterion_workspace_bytes(int64_t n);
+int sn_criterion_fwd(const void* pred, const void* y, int dtype, int64_t n, const float* ranges_host,
+                     const float* w_raw_host, int nbins, float mse_weight, double tversky_alpha,
+                     double tversky_beta, double focal_gamma, double tversky_smooth, int terms, double* loss,
+                     double* coef, void* ws, int64_t ws_bytes, void* stream);
+int sn_criterion_bwd(const void* pred, const void* y, int dtype, int64_t n, const float* ranges_host,
+                     const float* w_raw_host, int nbins, const double* coef, const void* grad_out,
+                     void* out, int out_g0, void* stream);
+/* Penalties on the live parameters (geneo_loss.py:36-71), float32, accumulated left to right like python's
+ * sum().  param_ptrs_host: HOST array of n DEVICE pointers to 0-dim float32 parameters; role_host[i]:
+ * 0 = relu(-v) regulariser term, 2 = free convex coefficient (relu(-v), and part of the coefficient sum),
+ * 1 = the frozen last coefficient (contributes relu(-(1 - sum(all coefficients) + itself))).
+ * out (DEVICE, 2 + n floats): [0] = weight * cvx_loss, [1] = weight * positive_regularizer,
+ * [2 + i] = d(out[0] + out[1]) / d param_i. */
+int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_host, int n, float weight,
+                     float* out, void* stream);
 
 /* ======================================================================================
  * elementwise helpers

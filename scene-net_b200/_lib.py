@@ -17,6 +17,8 @@ SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE = 0, 1, 2
 SN_MAX_GENEOS = 16
 SN_MAX_PARAM_PTRS = 96
 SN_MAX_TAPS = 4096
+SN_CRIT_MAX_BINS = 12
+SN_CRIT_COEF = SN_CRIT_MAX_BINS + 4
 ABI_VERSION = 2
 
 KIND = {
@@ -40,6 +42,7 @@ class ModelDesc(C.Structure):
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _descp = C.POINTER(ModelDesc)
 _pp = C.POINTER(C.c_void_p)
+_fp = C.POINTER(C.c_float)
 
 # name -> (restype, argtypes); must list every function include/scenenet_b200.h declares
 SIGNATURES = {
@@ -56,6 +59,10 @@ SIGNATURES = {
     "sn_scenenet_tapgrad_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_tapgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_grid_prepare": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "sn_criterion_workspace_bytes": (_i64, [_i64]),
+    "sn_criterion_fwd": (_i, [_vp, _vp, _i, _i64, _fp, _fp, _i, C.c_float, _d, _d, _d, _d, _i, _vp, _vp, _vp, _i64, _vp]),
+    "sn_criterion_bwd": (_i, [_vp, _vp, _i, _i64, _fp, _fp, _i, _vp, _vp, _vp, _i, _vp]),
+    "sn_param_penalty": (_i, [_pp, C.POINTER(C.c_int32), _i, C.c_float, _vp, _vp]),
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),

@@ -278,6 +278,86 @@ def tapgrad(x32: torch.Tensor, g0_: torch.Tensor, kernel_size, nnz: Optional[tor
     return W
 
 
+# ------------------------------------------------------------------------------- criterion
+@dataclass
+class CriterionSpec:
+    """Host-side constants of the fused GENEO_Tversky_Loss (include/scenenet_b200.h: sn_criterion_fwd)."""
+    ranges: Sequence[float]      # histogram bin positions (float32 values)
+    w_raw: Sequence[float]       # max(1 - weight_alpha * dens_k, weight_epsilon) per bin, float32
+    mse_weight: float = 1.0
+    tversky_alpha: float = 0.5
+    tversky_beta: float = 1.0
+    focal_gamma: float = 1.0
+    tversky_smooth: float = 1.0
+    terms: int = 3               # bit 0: weighted MSE, bit 1: focal Tversky
+
+    def arrays(self):
+        n = len(self.ranges)
+        if n != len(self.w_raw) or not 1 <= n <= _lib.SN_CRIT_MAX_BINS:
+            raise ValueError(f"between 1 and {_lib.SN_CRIT_MAX_BINS} histogram bins are supported, got {n}")
+        return (C.c_float * n)(*[float(v) for v in self.ranges]), (C.c_float * n)(*[float(v) for v in self.w_raw]), n
+
+
+def _crit_inputs(pred: torch.Tensor, y: torch.Tensor):
+    _need_cuda(pred, "y_pred")
+    _need_cuda(y, "y_gt")
+    if pred.dtype not in _DT:
+        raise TypeError(f"criterion: float32/float64 predictions only, got {pred.dtype}")
+    if y.shape != pred.shape:
+        pred, y = torch.broadcast_tensors(pred, y)
+    y = y.to(pred.dtype).contiguous()
+    pred = pred.contiguous()
+    if pred.data_ptr() % 16:
+        pred = pred.clone()
+    if y.data_ptr() % 16:
+        y = y.clone()
+    return pred, y
+
+
+def criterion_fwd(pred: torch.Tensor, y: torch.Tensor, spec: CriterionSpec):
+    """-> (loss [] float64, coef [SN_CRIT_COEF] float64, pred, y) — pred / y as handed to the kernel (contiguous)."""
+    pred, y = _crit_inputs(pred, y)
+    n = pred.numel()
+    if n == 0:
+        raise ValueError("criterion: empty tensors")
+    loss = torch.empty((), dtype=torch.float64, device=pred.device)
+    coef = torch.empty(_lib.SN_CRIT_COEF, dtype=torch.float64, device=pred.device)
+    ws = _workspace(int(lib.sn_criterion_workspace_bytes(n)), pred.device)
+    r, w, nb = spec.arrays()
+    with torch.cuda.device(pred.device):
+        check(lib.sn_criterion_fwd(pred.data_ptr(), y.data_ptr(), _DT[pred.dtype], n, r, w, nb, float(spec.mse_weight),
+                                   float(spec.tversky_alpha), float(spec.tversky_beta), float(spec.focal_gamma),
+                                   float(spec.tversky_smooth), int(spec.terms), loss.data_ptr(), coef.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream()), "sn_criterion_fwd")
+    return loss, coef, pred, y
+
+
+def criterion_bwd(pred: torch.Tensor, y: torch.Tensor, coef: torch.Tensor, spec: CriterionSpec,
+                  grad_out: Optional[torch.Tensor] = None, as_g0: bool = False) -> torch.Tensor:
+    """dL/dpred in pred's dtype, or (as_g0) G0 = dL/dpred * (1 - pred^2) * [pred > 0] as float32."""
+    out = torch.empty(pred.shape, dtype=torch.float32 if as_g0 else pred.dtype, device=pred.device)
+    if grad_out is not None:
+        grad_out = grad_out.to(pred.dtype).reshape(1)
+    r, w, nb = spec.arrays()
+    with torch.cuda.device(pred.device):
+        check(lib.sn_criterion_bwd(pred.data_ptr(), y.data_ptr(), _DT[pred.dtype], pred.numel(), r, w, nb, coef.data_ptr(),
+                                   _ptr(grad_out), out.data_ptr(), int(as_g0), _stream()), "sn_criterion_bwd")
+    return out
+
+
+def param_penalty(params: Sequence[torch.Tensor], roles: Sequence[int], weight: float) -> torch.Tensor:
+    """-> float32 [2 + n]: weight * cvx_loss, weight * positive_regularizer, d(sum of both)/d param_i."""
+    n = len(params)
+    if n > _lib.SN_MAX_PARAM_PTRS:
+        raise ValueError(f"at most {_lib.SN_MAX_PARAM_PTRS} parameters")
+    dev = params[0].device
+    out = torch.empty(2 + n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sn_param_penalty(_ptr_array(params), (C.c_int32 * n)(*[int(r) for r in roles]), n, float(weight),
+                                   out.data_ptr(), _stream()), "sn_param_penalty")
+    return out
+
+
 def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
     _need_cuda(p, "p")
     if p.dtype not in _DT:

@@ -139,8 +139,16 @@ def _x575(golden_dir):
     return (torch.from_numpy(x).view(1, 1, 64, 64, 64).to(DEV), torch.from_numpy(y).view(1, 1, 64, 64, 64).to(DEV))
 
 
+def _fused_criterion(pred, y, m):
+    """the drop-in GENEO_Tversky_Loss (fused kernels) with the hyper-parameters of the golden runs"""
+    crit = _sb().GENEO_Tversky_Loss(hist=(mo.HIST_FREQS, mo.HIST_RANGES), weight_alpha=1, weight_epsilon=0.1, mse_weight=1,
+                                    convex_weight=5, tversky_alpha=2, tversky_beta=1, focal_gamma=4, tversky_smooth=1e-6)
+    return crit(pred, y, m.get_cvx_coefficients(), m.get_geneo_params())
+
+
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("tag,v1", [("kat575", False), ("ckpt575", False), ("v1_575", True)])
-def test_config1_against_reference_outputs(golden_dir, tag, v1):
+def test_config1_against_reference_outputs(golden_dir, tag, v1, fused):
     gold = np.load(os.path.join(golden_dir, "ref_model.npz"))
     if tag == "ckpt575":
         cfg = json.loads(str(gold["ckpt|params"]))
@@ -152,7 +160,7 @@ def test_config1_against_reference_outputs(golden_dir, tag, v1):
     m = _make_model(params, lambdas, last, (9, 5, 5), v1=v1)
     pred = m(x)
     assert pred.dtype == torch.float64 and pred.shape == x.shape
-    loss = _criterion(pred, y, m)
+    loss = (_fused_criterion if fused else _criterion)(pred, y, m)
     loss.backward()
     p = pred.detach().cpu().numpy().reshape(-1)
     ref = np.zeros_like(p)
@@ -188,14 +196,16 @@ def test_synthetic_fixed_upstream_gradient(golden_dir, ks):
     print(f"{tag}: worst grad rel err {worst:.2e}")
 
 
-@pytest.mark.parametrize("tag", ["syn64_crit", "syn64_dpred"])
+@pytest.mark.parametrize("tag", ["syn64_crit", "syn64_crit_fused", "syn64_dpred"])
 def test_config2_shape_b2(golden_dir, tag):
+    fused = tag.endswith("_fused")
+    tag = tag.replace("_fused", "")
     gold = np.load(os.path.join(golden_dir, "ref_model.npz"))
     x, y = mo.synthetic_grids(2, (64, 64, 64), seed=1234)
     m = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
     pred = m(x.to(DEV))
     if tag == "syn64_crit":
-        loss = _criterion(pred, y.to(DEV), m)
+        loss = (_fused_criterion if fused else _criterion)(pred, y.to(DEV), m)
         loss.backward()
         rl = float(gold[f"{tag}|loss"])
         assert abs(float(loss) - rl) <= 1e-5 * abs(rl)
