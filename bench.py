@@ -141,19 +141,44 @@ def voxel_bench(device, hbm_gbs):
         b.synchronize()
         return a.elapsed_time(b) / reps * 1e-3
 
+    def graphed(fn):
+        """the same call captured once in a CUDA graph and replayed (fixed shapes: one cudaGraphLaunch per cloud batch)"""
+        s_ = torch.cuda.Stream(device=device)
+        s_.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(s_):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(s_)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()
+        return g, keep
+
     out = {}
     for n, grid in ((1_000_000, 64), (10_000_000, 128)):
         rows = cloud(n, 1)
-        dt = timeit(lambda: voxel_ops.voxelize_clouds(rows[:, :3], None, (grid,) * 3, rows[:, 3], [15], want=("occ", "occ_keep")))
+        call = lambda: voxel_ops.voxelize_clouds(rows[:, :3], None, (grid,) * 3, rows[:, 3], [15], want=("occ", "occ_keep"))
+        dt = timeit(call)
+        g, _keep = graphed(call)
+        dtg = timeit(g.replay)
         alg = 56 * n + 24 * grid ** 3
-        out[f"{n // 1_000_000}M_pts_{grid}^3"] = {"Mpts_per_s": n / dt / 1e6, "us": dt * 1e6, "algorithmic_GBps": alg / dt / 1e9,
-                                                   "hbm_frac": alg / dt / 1e9 / hbm_gbs}
-        del rows
+        out[f"{n // 1_000_000}M_pts_{grid}^3"] = {"Mpts_per_s": n / dtg / 1e6, "us": dtg * 1e6, "algorithmic_GBps": alg / dtg / 1e9,
+                                                   "hbm_frac": alg / dtg / 1e9 / hbm_gbs, "eager_us": dt * 1e6,
+                                                   "eager_Mpts_per_s": n / dt / 1e6}
+        del rows, g, _keep
     rows = torch.cat([cloud(60_000, s) for s in range(32)])
     off = torch.arange(0, 33, device=device, dtype=torch.int64) * 60_000
-    dt = timeit(lambda: voxel_ops.voxelize_clouds(rows[:, :3], off, (64, 64, 64), rows[:, 3], [15], want=("occ", "occ_keep")))
-    out["batch_32x60k_pts_64^3"] = {"Mpts_per_s": 32 * 60_000 / dt / 1e6, "clouds_per_s": 32 / dt, "us": dt * 1e6}
-    out["note"] = "eager calls (8 launches); algorithmic bytes = 56 B/point + 24 B/voxel (SURVEY 8d)"
+    call = lambda: voxel_ops.voxelize_clouds(rows[:, :3], off, (64, 64, 64), rows[:, 3], [15], want=("occ", "occ_keep"))
+    dt = timeit(call)
+    g, _keep = graphed(call)
+    dtg = timeit(g.replay)
+    alg = 56 * 32 * 60_000 + 24 * 32 * 64 ** 3
+    out["batch_32x60k_pts_64^3"] = {"Mpts_per_s": 32 * 60_000 / dtg / 1e6, "clouds_per_s": 32 / dtg, "us": dtg * 1e6,
+                                    "algorithmic_GBps": alg / dtg / 1e9, "hbm_frac": alg / dtg / 1e9 / hbm_gbs,
+                                    "eager_us": dt * 1e6, "eager_clouds_per_s": 32 / dt}
+    out["note"] = ("6 launches per call (bounding box, edges, grid init, binning, finalize), timed as CUDA-graph replays of the "
+                   "captured call (eager figures beside them are host-bound); algorithmic bytes = 56 B/point + 24 B/voxel (SURVEY 8d)")
     return out
 
 
@@ -458,7 +483,10 @@ def main():
             return a.elapsed_time(b) / reps * 1e-3
 
         g0s = [ops.g0(preds[i], pool[i][1]) for i in range(n_sets)]
-        t_fwd = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype))
+        from scenenet_b200._lib import SN_PATH_DENSE, SN_PATH_SPARSE
+        t_fwd = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype, mode=SN_PATH_DENSE))
+        t_fwd_sp = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype, mode=SN_PATH_SPARSE))
+        t_fwd_auto = time_kernel(lambda i: ops.scenenet_fwd(x32s[i % n_sets], Kstar, io_dtype, nnz=prep[i % n_sets][1]))
         t_g0 = time_kernel(lambda i: ops.g0(preds[i % n_sets], pool[i % n_sets][1]))
         # tap gradient (+ row reduction): the dense stencil, the occupancy-driven kernel, and what a step runs
         # (both enqueued, the device picks one from the non-zero count)

@@ -123,13 +123,21 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
 /* ======================================================================================
  * Observer forward — replaces F.conv3d + convex combination + relu(tanh) of
  * SceneNet.forward / SCENE_Net.forward (SCENE_Net.py:209-226, 322-339).
- *   x     [B,1,Z,X,Y] float32          (use sn_cast_f64_to_f32 for the reference's float64 grids)
+ *   x     [B,1,Z,X,Y] float32          (sn_grid_prepare converts the reference's float64 grids)
+ *   nnz   DEVICE pointer to the number of non-zero voxels of x (from sn_grid_prepare), or NULL
+ *   mode  SN_PATH_AUTO: with nnz, the dense stencil and an occupancy-driven kernel (cost proportional to the
+ *         occupied voxels) are both enqueued and the count selects ON THE DEVICE which of them works (sparse up
+ *         to 1.25 % occupancy for kx*ky <= 32 taps per slice, 4 % above); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
+ *         (measurement, tests).  Same pred either way up to float32 summation order.
  *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
  *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
  * x must be 16-byte aligned.
  * ====================================================================================== */
-int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z, int X, int Y, int kz, int kx, int ky,
-                    void* pred, int pred_dtype, void* stream);
+#define SN_PATH_AUTO 0
+#define SN_PATH_DENSE 1
+#define SN_PATH_SPARSE 2
+int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
+                    int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype, void* stream);
 
 /* Observer backward, data part — replaces aten::convolution_backward (weight gradient) and
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
@@ -154,9 +162,9 @@ int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, const void* p
  * sn_scenenet_bwd's workspace = G0 (n*4 bytes rounded up to 256) followed by the tap-gradient workspace.
  * mode: SN_TAPGRAD_AUTO (device-side selection from nnz; dense when nnz is NULL), SN_TAPGRAD_DENSE,
  *       SN_TAPGRAD_SPARSE (forced, nnz ignored; measurement and tests). */
-#define SN_TAPGRAD_AUTO 0
-#define SN_TAPGRAD_DENSE 1
-#define SN_TAPGRAD_SPARSE 2
+#define SN_TAPGRAD_AUTO SN_PATH_AUTO
+#define SN_TAPGRAD_DENSE SN_PATH_DENSE
+#define SN_TAPGRAD_SPARSE SN_PATH_SPARSE
 int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpred, int dpred_dtype, int64_t n, float* g0,
                    void* stream);
 int64_t sn_scenenet_tapgrad_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
@@ -226,11 +234,13 @@ int sn_threshold(const void* p, int dtype, double tau, int64_t n, void* out, voi
  * Points are float64 rows of `ld` doubles (x, y, z first; ld = 3 for an [N,3] array, ld = 4
  * for the TS40K .npy rows x,y,z,label of core/datasets/ts40k.py:207), labels float64 with
  * stride `label_ld` doubles (NULL = no labels).  Several clouds can be processed by one
- * launch: cloud c owns points [offsets[c], offsets[c+1]) and grid slice c.
+ * launch: cloud c owns points [offsets[c], offsets[c+1]) and grid slice c (offsets: DEVICE int64 [C+1];
+ * NULL with n_clouds == 1 = one cloud of n_points_total points).
  * ====================================================================================== */
 /* Step 1: per-cloud bounding box.  mnmx [C,6] float64 out = (xmin,ymin,zmin,xmax,ymax,zmax).
  * The buffer is initialised by the call itself. */
-int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, double* mnmx, void* stream);
+int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, int64_t n_points_total,
+                  double* mnmx, void* stream);
 
 /* Step 2: bin edges (np.linspace semantics: step=(hi-lo)/n rounded once, e[j]=fl(fl(j*step)+lo),
  * e[n]=hi) after the regular-bounding-box (cube) adjustment.  nx,ny,nz: voxelgrid_dims.

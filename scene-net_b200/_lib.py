@@ -13,6 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCENENET_B200_LIB", os.path.join(PKG, "libscenenet_b200.so"))  # override: experiments only
 
 SN_F32, SN_F64, SN_U8 = 0, 1, 2
+SN_PATH_AUTO, SN_PATH_DENSE, SN_PATH_SPARSE = 0, 1, 2
 SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE = 0, 1, 2
 SN_MAX_GENEOS = 16
 SN_MAX_PARAM_PTRS = 96
@@ -52,7 +53,7 @@ SIGNATURES = {
     "sn_geneo_synth_fwd": (_i, [_descp, _pp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sn_geneo_synth_bwd": (_i, [_descp, _pp, _vp, _vp, _vp]),
     "sn_scenenet_param_grads": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _vp]),
-    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_scenenet_g0": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
@@ -66,7 +67,7 @@ SIGNATURES = {
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),
-    "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_vox_edges": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sn_vox_bin": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sn_vox_finalize_workspace_bytes": (_i64, [_i, _i]),

@@ -31,7 +31,7 @@ class _ObserverFunction(torch.autograd.Function):
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         x32, nnz = ops.prepare(x.detach())
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
-        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
+        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz)
         ctx.spec = spec
         ctx.grad_scale = grad_scale
         ctx.sync_group = sync_group

@@ -45,6 +45,10 @@ struct FwdParams {
     // pass_mode bit 0: add the partial sum the previous pass left in pred; bit 1: store the raw partial sum
     // (no relu(tanh)) for the next pass.  Partial sums live in pred's own element slots (float -> double is exact).
     int plz, pass_mode;
+    // device-side selection against the occupancy-driven kernel (stencil_fwd_sparse.cu): this dense stencil returns
+    // at once when nnz != NULL and *nnz <= nnz_max
+    const unsigned long long* nnz;
+    unsigned long long nnz_max;
 };
 
 struct BwdParams {
@@ -68,6 +72,36 @@ struct BwdParams {
 // gradients are ill-conditioned sums of G0 (zero-sum projection), so float32 rounding inside this
 // product (dpred, tanh, 1-p^2) costs ~1e-5 relative on the worst gradient (scratch/precision_probe.py)
 __device__ __forceinline__ float g0_of(double p, double d) { return p > 0.0 ? (float)(d * (1.0 - p * p)) : 0.f; }
+
+// tanh(s) for s > 0 in float64 (~1e-11 relative), used by the occupancy-driven forward for float64 predictions.
+// Measured on the (7,7,7) reference fixture: the worst parameter gradient is 9.6e-6 of the reference with tanhf
+// in the dense stencil, 1.05e-5 with tanhf in the occupancy-driven kernel (another float32 summation order) and
+// 4.4e-6 with this evaluation — tanhf's 1-2 ulp error in pred is the largest single term of the error budget.
+// FP64 issue is scarce on B200: inside the FFMA-bound dense stencil this function costs +25 % (libm tanh(double):
+// +27 %; a variant with fewer FP64 operations but more selects / conversions: +38 %), so the dense stencil keeps
+// tanhf; the occupancy-driven kernel is not FP32-bound and pays +16 us at config 2 (profiles/r1_notes.md).
+// exp(2s) = 2^k * P(r), degree-11 Taylor on |r| <= ln2/2, then 1 - 2/(e + 1).
+__device__ __forceinline__ double tanh_pos_f64(double s) {
+    if (s > 20.0) return 1.0;
+    const double x = s + s;
+    const double kf = rint(x * 1.4426950408889634);
+    const double r = fma(-kf, 6.93147180369123816490e-01, x) - kf * 1.90821492927058770002e-10;  // ln2 hi / lo
+    double p = 2.5052108385441720e-08;  // 1/11!
+    p = fma(p, r, 2.7557319223985888e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.4801587301587302e-05);
+    p = fma(p, r, 1.9841269841269841e-04);
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kf;
+    const double e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // p * 2^k, k in [0, 58]
+    return 1.0 - 2.0 / (e + 1.0);
+}
 
 // tile geometry shared by host and device
 struct TileGeo {

@@ -20,16 +20,22 @@ int stencil_fwd_ky11(const FwdParams&, cudaStream_t);
 int stencil_fwd_ky13(const FwdParams&, cudaStream_t);
 int stencil_fwd_ky15(const FwdParams&, cudaStream_t);
 int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // stencil_generic.cu
+// stencil_fwd_sparse.cu
+bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
+int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
+                      unsigned long long nnz_max, int B, int Z, int X, int Y, int kz, int kx, int ky, cudaStream_t stream);
 }  // namespace sn
 
-extern "C" int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z, int X, int Y, int kz, int kx, int ky,
-                               void* pred, int pred_dtype, void* stream) {
-    if (!x || !Kstar || !pred) return SN_ERR_BAD_ARG;
-    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
-    if (pred_dtype != SN_F32 && pred_dtype != SN_F64) return SN_ERR_BAD_ARG;
-    if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
-    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0};
-    cudaStream_t s = (cudaStream_t)stream;
+// occupancy (percent of the voxels) up to which the occupancy-driven forward is selected (measured break-even,
+// scratch/time_sparse.py / profiles/r1_notes.md)
+// measured break-even on B200 (profiles/r1_notes.md, float64 predictions): (9,5,5) 1.3 %, (9,7,7) / 9^3 above 4 %
+static unsigned long long fwd_sparse_nnz_max(long long nvox, int kx, int ky) {
+    static const double forced = getenv("SN_SPARSE_FWD_PCT") ? atof(getenv("SN_SPARSE_FWD_PCT")) : -1.0;
+    const double pct = forced >= 0.0 ? forced : (kx * ky <= 32 ? 1.25 : 4.0);
+    return (unsigned long long)((double)nvox * pct / 100.0);
+}
+
+static int dense_fwd(const sn::FwdParams& p, int ky, cudaStream_t s) {
     int rc;
     switch (ky) {
         case 3: rc = sn::stencil_fwd_ky3(p, s); break;
@@ -42,6 +48,39 @@ extern "C" int sn_scenenet_fwd(const float* x, const float* Kstar, int B, int Z,
         case 15: rc = sn::stencil_fwd_ky15(p, s); break;
         default: rc = SN_ERR_UNSUPPORTED; break;
     }
-    if (rc == SN_ERR_UNSUPPORTED) rc = sn::stencil_fwd_generic(p, ky, s);
+    return rc;
+}
+
+extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
+                               int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype,
+                               void* stream) {
+    if (!x || !Kstar || !pred) return SN_ERR_BAD_ARG;
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    if (pred_dtype != SN_F32 && pred_dtype != SN_F64) return SN_ERR_BAD_ARG;
+    if (mode != SN_PATH_AUTO && mode != SN_PATH_DENSE && mode != SN_PATH_SPARSE) return SN_ERR_BAD_ARG;
+    if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
+    if (nnz && ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
+    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, nullptr, 0};
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool sparse_ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
+    const unsigned long long nnz_max = fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky);
+    if (mode == SN_PATH_SPARSE) {
+        if (!sparse_ok) return SN_ERR_UNSUPPORTED;
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+    }
+    if (mode == SN_PATH_AUTO && sparse_ok && nnz) {
+        // both kernels are enqueued; the non-zero count decides on the device which one works
+        p.nnz = nnz; p.nnz_max = nnz_max;
+        int rc = dense_fwd(p, ky, s);
+        if (rc == SN_ERR_UNSUPPORTED)  // no dense instantiation for this width: the occupancy-driven kernel always runs
+            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+        if (rc) return rc;
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, B, Z, X, Y, kz, kx, ky, s);
+    }
+    int rc = dense_fwd(p, ky, s);
+    if (rc == SN_ERR_UNSUPPORTED) {
+        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+        rc = sn::stencil_fwd_generic(p, ky, s);
+    }
     return rc;
 }

@@ -43,8 +43,8 @@ __device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __r
 // relu(tanh(s)) of one 4-voxel row segment + store.  Deliberately NOT inlined: 32 inlined tanhf bodies
 // were 13 KB of straight-line code next to the 23 KB tap loop and pushed the hot path out of the 32 KB
 // instruction cache level (profiles/r1_notes.md).
-// tanhf, not a float64 tanh: the double version cost ~27 % of the kernel's instructions and buys nothing
-// measurable (scratch/precision_probe.py: G0's float32 rounding in the backward dominates).
+// tanhf, not a float64 tanh: inside this FFMA-bound kernel every float64 variant tried cost +25 % .. +38 % of the
+// kernel (FP64 issue is scarce on B200; see tanh_pos_f64 in stencil_common.cuh, which the occupancy-driven kernel uses).
 static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, size_t idx, int out_f64, int ny,
                                        bool vec, int dbg, int pass_mode) {
     float o[4] = {a0, a1, a2, a3};
@@ -95,6 +95,7 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
 template <int KY, int TYT, int REM>
 __global__ void __launch_bounds__(kStencilThreads, 4)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
+    if (p.nnz && *p.nnz <= p.nnz_max) return;  // sparse input: fwd_sparse_kernel does the work
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);

@@ -16,6 +16,12 @@
 namespace sn {
 
 constexpr int kVoxThreads = 256;
+constexpr int kBinUnroll = 4;  // points per lane per step of the binning kernel
+// Per-CTA shared-memory aggregation table of the binning kernel: scan-coherent clouds send runs of points to the
+// same few thousand voxels, so a CTA that owns a CONTIGUOUS range of points first adds into a direct-mapped table
+// (native shared-memory integer atomics) and sends one global atomic per occupied slot at the end; a point whose
+// slot is taken by another voxel goes to global memory directly.  Integer adds: exact, order-independent.
+constexpr int kBinSlots = 4096;
 
 __device__ __forceinline__ void atomic_min_f64(double* a, double v) {
     unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
@@ -50,12 +56,14 @@ __global__ void minmax_init_kernel(double* mnmx, int n_clouds) {
 }
 
 __global__ void __launch_bounds__(kVoxThreads)
-minmax_kernel(const double* __restrict__ pts, int ld, const long long* __restrict__ offsets, double* __restrict__ mnmx) {
+minmax_kernel(const double* __restrict__ pts, int ld, const long long* __restrict__ offsets, long long n_total,
+              double* __restrict__ mnmx) {
     __shared__ double red[6][kVoxThreads / 32];
     const int c = blockIdx.y;
-    const long long beg = offsets[c], end = offsets[c + 1];
+    const long long beg = offsets ? offsets[c] : 0, end = offsets ? offsets[c + 1] : n_total;
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     const bool vec4 = (ld == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
+#pragma unroll 4
     for (long long i = beg + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long long)gridDim.x * blockDim.x) {
         double v[3];
         if (vec4) {
@@ -139,12 +147,22 @@ __global__ void bin_init_kernel(int* __restrict__ count, int* __restrict__ keep_
     }
 }
 
-// largest j with e[j] < p, or 0 if none; == clip(searchsorted(e, p, 'left') - 1, 0, n-1) for p <= e[n]
+// largest j with e[j] < p, or 0 if none; == clip(searchsorted(e, p, 'left') - 1, 0, n-1) for p <= e[n].
+// The multiply gives the bin up to +-1 (rounding): the common case is decided by two edge compares without a
+// loop; the loops only run when the guess was off.
 __device__ __forceinline__ int bin_of(const double* __restrict__ e, int n, double p, double lo, double inv_step) {
     int j = (int)((p - lo) * inv_step);
     j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
-    while (j + 1 <= n - 1 && e[j + 1] < p) ++j;
-    while (j > 0 && !(e[j] < p)) --j;
+    const double ej = e[j], ej1 = e[j + 1];  // e has n + 1 entries
+    const bool down = j > 0 && !(ej < p);
+    const bool up = j + 1 <= n - 1 && ej1 < p;
+    if (down) {
+        --j;
+        while (j > 0 && !(e[j] < p)) --j;
+    } else if (up) {
+        ++j;
+        while (j + 1 <= n - 1 && e[j + 1] < p) ++j;
+    }
     return j;
 }
 
@@ -152,63 +170,106 @@ __global__ void __launch_bounds__(kVoxThreads)
 bin_kernel(const double* __restrict__ pts, int ld, const double* __restrict__ labels, int label_ld,
            const long long* __restrict__ offsets, const double* __restrict__ edges, int nx, int ny, int nz,
            const double* __restrict__ keep, int n_keep, int* __restrict__ count, int* __restrict__ keep_count,
-           long long* __restrict__ maxkey, int* __restrict__ lin_out) {
-    extern __shared__ double s_edges[];  // (nx+1)+(ny+1)+(nz+1) doubles, then n_keep keep labels
+           long long* __restrict__ maxkey, int* __restrict__ lin_out, long long n_total) {
+    extern __shared__ double s_edges[];  // (nx+1)+(ny+1)+(nz+1) doubles, n_keep keep labels, then the aggregation table
     const int c = blockIdx.y;
     const int ne = nx + ny + nz + 3;
     for (int i = threadIdx.x; i < ne; i += blockDim.x) s_edges[i] = edges[(size_t)c * ne + i];
     double* s_keep = s_edges + ne;
     for (int i = threadIdx.x; i < n_keep; i += blockDim.x) s_keep[i] = keep[i];
+    int* s_key = reinterpret_cast<int*>(s_keep + n_keep + (n_keep & 1));  // table behind the doubles
+    int* s_cnt = s_key + kBinSlots;
+    int* s_kcnt = s_cnt + kBinSlots;
+    for (int i = threadIdx.x; i < kBinSlots; i += blockDim.x) {
+        s_key[i] = -1;
+        s_cnt[i] = 0;
+        s_kcnt[i] = 0;
+    }
     __syncthreads();
     const double* ex = s_edges;
     const double* ey = s_edges + nx + 1;
     const double* ez = ey + ny + 1;
     const double lox = ex[0], loy = ey[0], loz = ez[0];
     const double ivx = (double)nx / (ex[nx] - lox), ivy = (double)ny / (ey[ny] - loy), ivz = (double)nz / (ez[nz] - loz);
-    const long long beg = offsets[c], end = offsets[c + 1];
+    const long long cbeg = offsets ? offsets[c] : 0, cend = offsets ? offsets[c + 1] : n_total;
+    // this CTA's contiguous range of the cloud's points (multiples of a warp step)
+    const long long step = 32LL * kBinUnroll;
+    const long long per = ceil_div64(ceil_div64(cend - cbeg, (long long)gridDim.x), step) * step;
+    const long long beg = cbeg + (long long)blockIdx.x * per;
+    const long long end = beg + per < cend ? beg + per : cend;
     const long long V = (long long)nx * ny * nz;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool vec4 = (ld == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
     const bool lab_in_row = vec4 && labels == pts + 3 && label_ld == 4;
+    int* count_c = count + (size_t)c * V;
+    int* keep_c = keep_count ? keep_count + (size_t)c * V : nullptr;
 
-    for (long long base = beg + (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < end;
-         base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + lane;
-        const bool valid = i < end;
-        const unsigned mask = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
-        double px, py, pz, lab = 0.0;
-        if (vec4) {
-            const double2 a = __ldg(reinterpret_cast<const double2*>(pts + i * 4));
-            const double2 b = __ldg(reinterpret_cast<const double2*>(pts + i * 4) + 1);
-            px = a.x; py = a.y; pz = b.x;
-            if (lab_in_row) lab = b.y;
-        } else {
-            const double* q = pts + i * ld;
-            px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+    // kBinUnroll points per lane per step, all loads issued before the first use: with one point in flight per
+    // thread the kernel was bound by the HBM latency of its own loads
+    for (long long base = beg + (long long)warp * step; base < end; base += (long long)nwarps * step) {
+        double px[kBinUnroll], py[kBinUnroll], pz[kBinUnroll], lab[kBinUnroll];
+        bool valid[kBinUnroll];
+#pragma unroll
+        for (int u = 0; u < kBinUnroll; ++u) {
+            const long long i = base + 32 * u + lane;
+            valid[u] = i < end;
+            px[u] = py[u] = pz[u] = lab[u] = 0.0;
+            if (valid[u]) {
+                if (vec4) {
+                    const double2 a = __ldg(reinterpret_cast<const double2*>(pts + i * 4));
+                    const double2 b = __ldg(reinterpret_cast<const double2*>(pts + i * 4) + 1);
+                    px[u] = a.x; py[u] = a.y; pz[u] = b.x;
+                    if (lab_in_row) lab[u] = b.y;
+                } else {
+                    const double* q = pts + i * ld;
+                    px[u] = __ldg(q); py[u] = __ldg(q + 1); pz[u] = __ldg(q + 2);
+                }
+                if (labels && !lab_in_row) lab[u] = __ldg(labels + i * label_ld);
+            }
         }
-        if (labels && !lab_in_row) lab = __ldg(labels + i * label_ld);
-        const int vx = bin_of(ex, nx, px, lox, ivx);
-        const int vy = bin_of(ey, ny, py, loy, ivy);
-        const int vz = bin_of(ez, nz, pz, loz, ivz);
-        const int lin = (vz * nx + vx) * ny + vy;  // reference grid layout data[z, x, y]
-        if (lin_out) lin_out[i] = lin;
-        bool is_keep = false;
-        if (labels)
-            for (int k = 0; k < n_keep; ++k) is_keep |= (lab == s_keep[k]);
-        // warp-aggregated atomics: one atomicAdd per distinct voxel per warp
-        const unsigned peers = __match_any_sync(mask, lin);
-        const unsigned kmask = __ballot_sync(mask, is_keep);
-        const bool leader = (__ffs(peers) - 1) == lane;
-        const long long g = (long long)c * V + lin;
-        if (leader) {
-            atomicAdd(&count[g], __popc(peers));
-            const int kc = __popc(peers & kmask);
-            if (keep_count && kc) atomicAdd(&keep_count[g], kc);
+#pragma unroll
+        for (int u = 0; u < kBinUnroll; ++u) {
+            const unsigned mask = __ballot_sync(0xffffffffu, valid[u]);
+            if (!valid[u]) continue;
+            const long long i = base + 32 * u + lane;
+            const int vx = bin_of(ex, nx, px[u], lox, ivx);
+            const int vy = bin_of(ey, ny, py[u], loy, ivy);
+            const int vz = bin_of(ez, nz, pz[u], loz, ivz);
+            const int lin = (vz * nx + vx) * ny + vy;  // reference grid layout data[z, x, y]
+            if (lin_out) lin_out[i] = lin;
+            bool is_keep = false;
+            if (labels)
+                for (int k = 0; k < n_keep; ++k) is_keep |= (lab[u] == s_keep[k]);
+            // warp-aggregated: one table / global update per distinct voxel per warp
+            const unsigned peers = __match_any_sync(mask, lin);
+            const unsigned kmask = __ballot_sync(mask, is_keep);
+            const bool leader = (__ffs(peers) - 1) == lane;
+            if (leader) {
+                const int nc = __popc(peers), kc = __popc(peers & kmask);
+                const int slot = (int)(((unsigned)lin * 2654435761u) >> (32 - 12));  // kBinSlots = 2^12
+                const int old = atomicCAS(&s_key[slot], -1, lin);
+                if (old == -1 || old == lin) {
+                    atomicAdd(&s_cnt[slot], nc);
+                    if (keep_c && kc) atomicAdd(&s_kcnt[slot], kc);
+                } else {
+                    atomicAdd(&count_c[lin], nc);
+                    if (keep_c && kc) atomicAdd(&keep_c[lin], kc);
+                }
+            }
+            if (maxkey && labels) {
+                const long long g = (long long)c * V + lin;
+                const long long k = f64_key(lab[u]);
+                if (k > *reinterpret_cast<volatile long long*>(&maxkey[g])) atomicMax(&maxkey[g], k);  // cheap pre-check, most points lose
+            }
         }
-        if (maxkey && labels) {
-            const long long k = f64_key(lab);
-            if (k > *reinterpret_cast<volatile long long*>(&maxkey[g])) atomicMax(&maxkey[g], k);  // cheap pre-check, most points lose
+    }
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < kBinSlots; sl += blockDim.x) {
+        const int key = s_key[sl];
+        if (key >= 0) {
+            atomicAdd(&count_c[key], s_cnt[sl]);
+            const int kc = s_kcnt[sl];
+            if (keep_c && kc) atomicAdd(&keep_c[key], kc);
         }
     }
 }
@@ -280,14 +341,16 @@ static inline int blocks_for(long long n, int cap_mult = 8) {
 
 }  // namespace sn
 
-extern "C" int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, double* mnmx, void* stream) {
-    if (!pts || !offsets || !mnmx || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+extern "C" int sn_vox_minmax(const double* pts, int ld, const int64_t* offsets, int n_clouds, int64_t n_points_total,
+                             double* mnmx, void* stream) {
+    if (!pts || !mnmx || ld < 3 || n_clouds < 1 || n_clouds > 65535 || n_points_total < 0) return SN_ERR_BAD_ARG;
+    if (!offsets && n_clouds != 1) return SN_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     sn::minmax_init_kernel<<<sn::ceil_div(n_clouds * 6, 128), 128, 0, s>>>(mnmx, n_clouds);
     SN_LAUNCH_CHECK();
     // offsets live on the device: size the grid for the machine, blocks grid-stride over their cloud
     const int bx = max(1, sn::kNumSMs * 4 / n_clouds);
-    sn::minmax_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, 0, s>>>(pts, ld, (const long long*)offsets, mnmx);
+    sn::minmax_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, 0, s>>>(pts, ld, (const long long*)offsets, n_points_total, mnmx);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -303,24 +366,27 @@ extern "C" int sn_vox_bin(const double* pts, int ld, const double* labels, int l
                           int n_clouds, int64_t n_points_total, const double* edges, int nx, int ny, int nz,
                           const double* keep, int n_keep, int32_t* count, int32_t* keep_count, double* max_label,
                           int32_t* lin_out, void* stream) {
-    if (!pts || !offsets || !edges || !count || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+    if (!pts || !edges || !count || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+    if (!offsets && n_clouds != 1) return SN_ERR_BAD_ARG;
     if (nx < 1 || ny < 1 || nz < 1 || n_keep < 0 || (n_keep > 0 && !keep) || n_points_total < 0) return SN_ERR_BAD_ARG;
     if ((long long)nx * ny * nz > 0x7fffffffLL) return SN_ERR_UNSUPPORTED;
     if (labels && label_ld < 1) return SN_ERR_BAD_ARG;
-    const size_t smem = (size_t)(nx + ny + nz + 3 + n_keep) * sizeof(double);
-    if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
+    if ((size_t)(nx + ny + nz + 3 + n_keep) * sizeof(double) > 48 * 1024) return SN_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(nx + ny + nz + 3 + n_keep + (n_keep & 1)) * sizeof(double) + 3 * sn::kBinSlots * sizeof(int);
+    cudaError_t ea = cudaFuncSetAttribute(sn::bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return sn::cuda_rc(ea);
     cudaStream_t s = (cudaStream_t)stream;
     const long long nvox = (long long)n_clouds * nx * ny * nz;
     sn::bin_init_kernel<<<sn::blocks_for(nvox), sn::kVoxThreads, 0, s>>>(count, keep_count, (long long*)max_label, nvox);
     SN_LAUNCH_CHECK();
     if (n_points_total == 0) return SN_OK;
     const long long per_cloud = sn::ceil_div64(n_points_total, n_clouds);
-    int bx = (int)sn::ceil_div64(per_cloud, sn::kVoxThreads);
+    int bx = (int)sn::ceil_div64(per_cloud, sn::kVoxThreads * sn::kBinUnroll);
     const int cap = max(1, sn::kNumSMs * 8 / n_clouds);
     bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
     sn::bin_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, smem, s>>>(pts, ld, labels, label_ld, (const long long*)offsets, edges,
                                                                     nx, ny, nz, keep, n_keep, count, keep_count,
-                                                                    (long long*)max_label, lin_out);
+                                                                    (long long*)max_label, lin_out, n_points_total);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -204,7 +204,10 @@ def _grid_dims(x: torch.Tensor):
     return int(B), int(Z), int(X), int(Y)
 
 
-def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype, nnz: Optional[torch.Tensor] = None,
+                 mode: int = 0) -> torch.Tensor:
+    """pred = relu(tanh(conv3d_same(x, Kstar))).  nnz (from `prepare`) enables the device-side choice of the
+    occupancy-driven kernel; mode: _lib.SN_PATH_AUTO / _DENSE / _SPARSE."""
     _need_cuda(x32, "x")
     B, Z, X, Y = _grid_dims(x32)
     kz, kx, ky = (int(v) for v in Kstar.shape)
@@ -212,8 +215,8 @@ def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype)
     if x32.numel() == 0:
         return pred
     with torch.cuda.device(x32.device):
-        check(lib.sn_scenenet_fwd(x32.data_ptr(), Kstar.data_ptr(), B, Z, X, Y, kz, kx, ky, pred.data_ptr(), _DT[out_dtype],
-                                  _stream()), "sn_scenenet_fwd")
+        check(lib.sn_scenenet_fwd(x32.data_ptr(), _ptr(nnz), int(mode), Kstar.data_ptr(), B, Z, X, Y, kz, kx, ky, pred.data_ptr(),
+                                  _DT[out_dtype], _stream()), "sn_scenenet_fwd")
     return pred
 
 

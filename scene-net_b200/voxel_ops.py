@@ -29,13 +29,13 @@ def _keep_tensor(keep: Optional[Sequence[float]], device) -> Optional[torch.Tens
     return t
 
 
-def bounding_boxes(points: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
-    """[C,6] float64 (xmin,ymin,zmin,xmax,ymax,zmax) per cloud."""
+def bounding_boxes(points: torch.Tensor, offsets: Optional[torch.Tensor]) -> torch.Tensor:
+    """[C,6] float64 (xmin,ymin,zmin,xmax,ymax,zmax) per cloud (offsets None = one cloud)."""
     _need_cuda(points, "points")
-    C_ = offsets.numel() - 1
+    C_ = 1 if offsets is None else offsets.numel() - 1
     out = torch.empty((C_, 6), dtype=torch.float64, device=points.device)
     with torch.cuda.device(points.device):
-        check(lib.sn_vox_minmax(points.data_ptr(), points.stride(0), offsets.data_ptr(), C_, out.data_ptr(), _stream()),
+        check(lib.sn_vox_minmax(points.data_ptr(), points.stride(0), _ptr(offsets), C_, points.shape[0], out.data_ptr(), _stream()),
               "sn_vox_minmax")
     return out
 
@@ -63,9 +63,7 @@ def voxelize_clouds(points: torch.Tensor, offsets: Optional[torch.Tensor] = None
         raise TypeError("points must be float64 [N, >=3] with unit inner stride")
     dev = points.device
     N = points.shape[0]
-    if offsets is None:
-        offsets = torch.tensor([0, N], dtype=torch.int64, device=dev)
-    C_ = offsets.numel() - 1
+    C_ = 1 if offsets is None else offsets.numel() - 1  # one cloud: no offsets tensor (no host->device copy per call)
     nx, ny, nz = (int(v) for v in grid_xyz)
     want = set(want)
     if labels is not None:
@@ -86,7 +84,7 @@ def voxelize_clouds(points: torch.Tensor, offsets: Optional[torch.Tensor] = None
         maxlab = torch.empty(shape, dtype=torch.float64, device=dev) if "max_label" in want else None
         lin = torch.empty(N, dtype=torch.int32, device=dev) if return_lin else None
         check(lib.sn_vox_bin(points.data_ptr(), points.stride(0), _ptr(labels), labels.stride(0) if labels is not None else 0,
-                             offsets.data_ptr(), C_, N, edges.data_ptr(), nx, ny, nz, _ptr(keep_t),
+                             _ptr(offsets), C_, N, edges.data_ptr(), nx, ny, nz, _ptr(keep_t),
                              0 if keep_t is None else keep_t.numel(), count.data_ptr(), _ptr(keep_count), _ptr(maxlab),
                              _ptr(lin), _stream()), "sn_vox_bin")
         density = torch.empty(shape, dtype=torch.float64, device=dev) if "density" in want else None
