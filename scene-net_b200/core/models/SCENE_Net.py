@@ -23,13 +23,30 @@ from .geneos import arrow, cylinder, neg_sphere
 from .geneos.GENEO_kernel_torch import GENEO_kernel_torch
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
 class _ObserverFunction(torch.autograd.Function):
     """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
 
     @staticmethod
     def forward(ctx, x, spec, write_last, grad_scale, sync_group, *params):
+        # kernel synthesis (one latency-bound CTA) and grid preparation (HBM-bound) are independent: the preparation
+        # runs on a side stream (a parallel branch when the step is captured in a CUDA graph)
+        cur = torch.cuda.current_stream(x.device)
+        side = _side_stream(x.device)
+        x32, nnz = ops.prepare(x.detach(), stream=side)  # buffers belong to the current stream, the pass runs on `side`
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
-        x32, nnz = ops.prepare(x.detach())
+        cur.wait_stream(side)
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz)
         ctx.spec = spec

@@ -119,21 +119,32 @@ __global__ void __launch_bounds__(kCritThreads) crit_reduce_kernel(const T* __re
     }
 }
 
-// One warp: sums the partial rows in order, then lane 0 does the scalar arithmetic.
+// One CTA: sums the partial rows in a fixed order, then thread 0 does the scalar arithmetic.
 // coef: [0, nb) a_k = d(dense)/dp = a_k * (p - y) for a voxel of bin k; [MAX] tvY; [MAX+1] tvN:
 //       d(focal tversky)/dp = tvY * y + tvN * (1 - y);  [MAX+2] dense term, [MAX+3] focal tversky term (diagnostics)
-__global__ void __launch_bounds__(32) crit_finalize_kernel(const double* __restrict__ partial, int rows, long long n,
-                                                           const __grid_constant__ CritTable tab, float mse_weight,
-                                                           double tv_alpha, double tv_beta, double gamma, double smooth,
-                                                           int terms, double* __restrict__ loss, double* __restrict__ coef) {
+__global__ void __launch_bounds__(1024) crit_finalize_kernel(const double* __restrict__ partial, int rows, long long n,
+                                                             const __grid_constant__ CritTable tab, float mse_weight,
+                                                             double tv_alpha, double tv_beta, double gamma, double smooth,
+                                                             int terms, double* __restrict__ loss, double* __restrict__ coef) {
+    // 32 row groups x 32 columns: every thread sums its rows in order, then one thread per column sums the 32 group
+    // sums in order (a single warp walking all rows took 28 us: one dependent load chain per column)
+    __shared__ double s_grp[32][kCritRow + 1];
     __shared__ double s_tot[kCritRow];
-    const int lane = threadIdx.x;
-    for (int c = lane; c < kCritRow; c += 32) {
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    for (int cc = c; cc < kCritRow; cc += 32) {
         double a = 0.0;
-        for (int r = 0; r < rows; ++r) a += partial[(size_t)r * kCritRow + c];
-        s_tot[c] = a;
+        for (int r = g; r < rows; r += 32) a += partial[(size_t)r * kCritRow + cc];
+        s_grp[g][cc] = a;
     }
-    __syncwarp();
+    __syncthreads();
+    if (threadIdx.x < kCritRow) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a += s_grp[i][threadIdx.x];
+        s_tot[threadIdx.x] = a;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x;
     if (lane != 0) return;
     const int nb = tab.nbins;
     // weights / mean(weights): float32 tensors in the reference (w_mse.py:141-145)
@@ -222,12 +233,15 @@ struct PenaltyArgs {
     signed char role[SN_MAX_PARAM_PTRS];
     int n;
 };
-__global__ void penalty_kernel(const __grid_constant__ PenaltyArgs a, float weight, float* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(128) penalty_kernel(const __grid_constant__ PenaltyArgs a, float weight, float* __restrict__ out) {
+    __shared__ float s_v[SN_MAX_PARAM_PTRS];
+    if (threadIdx.x < a.n) s_v[threadIdx.x] = *a.p[threadIdx.x];  // all parameter loads in flight at once
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     float pos = 0.f, cvx = 0.f, lsum = 0.f, last = 0.f;
     bool has_last = false;
     for (int i = 0; i < a.n; ++i) {
-        const float v = *a.p[i];
+        const float v = s_v[i];
         const int r = a.role[i];
         float g = 0.f;
         if (r == 0) {
@@ -302,7 +316,7 @@ extern "C" int sn_criterion_fwd(const void* pred, const void* y, int dtype, int6
     else
         sn::crit_reduce_kernel<float><<<grid, sn::kCritThreads, 0, s>>>((const float*)pred, (const float*)y, n, t, partial);
     SN_LAUNCH_CHECK();
-    sn::crit_finalize_kernel<<<1, 32, 0, s>>>(partial, grid, n, t, mse_weight, tversky_alpha, tversky_beta, focal_gamma,
+    sn::crit_finalize_kernel<<<1, 1024, 0, s>>>(partial, grid, n, t, mse_weight, tversky_alpha, tversky_beta, focal_gamma,
                                               tversky_smooth, terms, loss, coef);
     SN_LAUNCH_CHECK();
     return SN_OK;
@@ -350,7 +364,7 @@ extern "C" int sn_param_penalty(const float* const* param_ptrs_host, const int32
         }
     }
     if (n_last > 1) return SN_ERR_BAD_ARG;
-    sn::penalty_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, weight, out);
+    sn::penalty_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(a, weight, out);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -174,10 +174,12 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def prepare(x: torch.Tensor):
+def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
     (x itself for float32 input), nnz a 1-element int64 device tensor with the number of non-zero voxels: the
-    backward uses it ON THE DEVICE to pick the occupancy-driven tap-gradient kernel for sparse grids."""
+    forward and the backward use it ON THE DEVICE to pick the occupancy-driven kernels for sparse grids.
+    stream: run the pass on this (side) stream after everything enqueued so far on the current one; the outputs
+    are allocated on the current stream and the caller joins the streams (`current.wait_stream(stream)`)."""
     _need_cuda(x, "x")
     if x.dtype == torch.bool:
         x = x.view(torch.uint8)
@@ -192,8 +194,11 @@ def prepare(x: torch.Tensor):
     nnz = torch.empty(1, dtype=torch.int64, device=x.device)
     dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
     with torch.cuda.device(x.device):
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(x.device))  # x (and any copy made above) is ready
+        st = _stream() if stream is None else stream.cuda_stream
         check(lib.sn_grid_prepare(x.data_ptr(), dt, x.numel(), None if x.dtype == torch.float32 else x32.data_ptr(),
-                                  nnz.data_ptr(), _stream()), "sn_grid_prepare")
+                                  nnz.data_ptr(), st), "sn_grid_prepare")
     return x32, nnz
 
 
