@@ -265,8 +265,24 @@ def main():
     model = kat_model(device)
     trainable = [p for p in model.parameters() if p.requires_grad]
     model.grad_scale = 1.0 / world  # DDP mean folded into the Jacobian kernel; the collective only sums
+    grad_allreduce = None
     if world > 1:
-        model.grad_sync_group = True  # one all-reduce of the flat 13-float payload inside backward
+        # one all-reduce of the flat 13-float payload inside backward: our single-kernel exchange over NVLink peer
+        # memory when the peer mappings are available, else NCCL
+        try:
+            if os.environ.get("SN_BENCH_NCCL"):
+                raise RuntimeError("forced by SN_BENCH_NCCL")
+            model.grad_sync_group = sdist.PeerAllReduce(device)
+            grad_allreduce = "sn_peer_allreduce (one kernel over NVLink peer memory)"
+        except Exception as e:  # noqa: BLE001
+            model.grad_sync_group = True
+            grad_allreduce = f"ncclAllReduce (peer memory unavailable: {type(e).__name__}: {str(e)[:80]})"
+        # every rank must take the same path
+        flag = torch.tensor([1 if callable(model.grad_sync_group) else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0 and callable(model.grad_sync_group):
+            model.grad_sync_group = True
+            grad_allreduce = "ncclAllReduce (peer memory unavailable on another rank)"
 
     bytes_per_set = B_PER_GPU * GRID[0] * GRID[1] * GRID[2] * (8 if io_dtype == torch.float64 else 4) * 3
     n_sets = max(3, -(-4 * L2_BYTES // bytes_per_set))
@@ -450,6 +466,15 @@ def main():
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         grad_sync_ok = bool(all(torch.equal(g, gathered[0]) for g in gathered)) and bool(flat.abs().sum() > 0)
+        if callable(model.grad_sync_group):
+            # the peer-memory exchange against NCCL on the same per-rank payload
+            grad_sync_ok = grad_sync_ok and model.grad_sync_group.ok()
+            probe = torch.arange(1, 14, device=device, dtype=torch.float32) * (rank + 1) * 0.37
+            ref = probe.clone()
+            dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+            model.grad_sync_group(probe)
+            torch.cuda.synchronize()
+            grad_sync_ok = grad_sync_ok and bool(torch.allclose(probe, ref, rtol=1e-6, atol=0))
     barrier()
     if world > 1 and rank != 0:
         sys.stdout.flush()
@@ -531,7 +556,7 @@ def main():
             "config": {"workload": "SCENE-Net training step fwd+bwd (13 params, 11 trainable), batch 32 per GPU of synthetic "
                                    "TS40K-shaped 64^3 occupancy grids (Bernoulli 0.016), kernel (9,5,5), G=3, fixed upstream "
                                    "dL/dpred ~ N(0,1) (BASELINE config 2)",
-                       "global_batch": B_PER_GPU * world, "io_dtype": args.io_dtype, "parallelism": f"dp{world}",
+                       "global_batch": B_PER_GPU * world, "io_dtype": args.io_dtype, "parallelism": f"dp{world}", "grad_allreduce": grad_allreduce,
                        "launch": "eager module calls" if args.eager else "CUDA-graph replay of the captured module step (scenenet_b200.graphs.GraphedStep)",
                        "eager_module_value": eager_value,
                        "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},

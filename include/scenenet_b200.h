@@ -267,6 +267,27 @@ int sn_vox_finalize(const int32_t* count, const int32_t* keep_count, int n_cloud
                     int out_dtype, void* ws, void* stream);
 
 /* ======================================================================================
+ * Multi-GPU: all-reduce (sum) of the parameter-gradient payload over NVLink peer memory.
+ * Replaces the gradient all-reduce Lightning's implicit DDP performs for the reference
+ * (scripts/main.py:224-236) — 11..96 floats per step, pure latency — by ONE single-CTA kernel:
+ * every rank stores its payload into every peer's exchange buffer, raises a flag, waits for
+ * the peers' flags in its own buffer and adds the payloads in rank order (bit-identical
+ * result on all ranks, deterministic).
+ *   data            [n] float32 DEVICE, in place (n <= SN_MAX_PARAM_PTRS)
+ *   peer_bufs_host  HOST array of `world` DEVICE pointers: entry w = rank w's exchange buffer of
+ *                   sn_peer_allreduce_buffer_bytes(world) bytes, peer-mapped into this process
+ *                   (e.g. torch symmetric memory), zero-initialised before the first call
+ *   seq_counter     DEVICE uint32, local, zero-initialised: the call sequence number (the kernel
+ *                   increments it, so a captured CUDA graph can be replayed as is)
+ *   status          DEVICE int32 (may be NULL): set to 1 if a peer did not answer within ~2 s
+ *                   (the payload is then NaN; the device is never left spinning)
+ * Every rank must issue the same sequence of calls.
+ * ====================================================================================== */
+int64_t sn_peer_allreduce_buffer_bytes(int world);
+int sn_peer_allreduce(float* data, int n, int rank, int world, const uint64_t* peer_bufs_host,
+                      uint32_t* seq_counter, int32_t* status, void* stream);
+
+/* ======================================================================================
  * measurement helper: FP32 FMA-pipe peak micro-benchmark (the roofline denominator that
  * MEASURED_PEAKS.json lacks).  Runs `iters` dependent-chain FFMA rounds on every
  * SM; the caller times it with CUDA events.  flops_out (host) receives the FLOPs issued. */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "sn_vox_bin": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sn_vox_finalize_workspace_bytes": (_i64, [_i, _i]),
     "sn_vox_finalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sn_peer_allreduce_buffer_bytes": (_i64, [_i]),
+    "sn_peer_allreduce": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64), _vp, _vp, _vp]),
     "sn_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(C.c_double), _vp]),
 }
 

@@ -63,8 +63,11 @@ class _ObserverFunction(torch.autograd.Function):
         if ctx.sync_group is not None:
             # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
             # no pack / unpack kernels; the parameter .grads are views into it
-            import torch.distributed as dist
-            dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
+            if callable(ctx.sync_group):
+                ctx.sync_group(d)  # dist.PeerAllReduce: our single-kernel exchange over NVLink peer memory
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
         unused = ctx.spec.unused
         grads = [d[i] if (ctx.needs_input_grad[i + 5] and i not in unused) else None for i in range(d.numel())]
         return (None, None, None, None, None, *grads)

@@ -48,3 +48,50 @@ def allreduce_mean_grads(params: Sequence[torch.nn.Parameter], group=None, alrea
         flat /= dist.get_world_size(group)
     for p, g in zip(ps, flat.unbind()):
         p.grad.copy_(g)
+
+
+class PeerAllReduce:
+    """Sum of a small float32 vector over the ranks of `group` through NVLink peer memory (csrc/peer_allreduce.cu):
+    one single-CTA kernel per call instead of an NCCL collective — the gradient payload is <= 96 floats, so the
+    collective is pure latency.  torch's symmetric memory is the plumbing (allocation + exchange of the peer
+    mappings); the data path is our kernel.  Raises at construction when peer memory is not available (the caller
+    then keeps the NCCL all-reduce)."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import check, lib
+        group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = int(lib.sn_peer_allreduce_buffer_bytes(self.world))
+        if nbytes < 0:
+            raise RuntimeError(f"peer all-reduce supports at most 16 ranks, got {self.world}")
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric-memory rendezvous returned no peer mappings")
+        self.ptrs = (C.c_uint64 * self.world)(*ptrs)
+        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self._check, self._lib = check, lib
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffer is zeroed and mapped before the first exchange
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        """in-place sum over ranks of a contiguous float32 CUDA vector (<= 96 elements)"""
+        if flat.dtype != torch.float32 or not flat.is_cuda or not flat.is_contiguous():
+            raise TypeError("peer all-reduce: contiguous float32 CUDA vector expected")
+        with torch.cuda.device(flat.device):
+            self._check(self._lib.sn_peer_allreduce(flat.data_ptr(), flat.numel(), self.rank, self.world, self.ptrs,
+                                                    self.seq.data_ptr(), self.status.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "sn_peer_allreduce")
+        return flat
+
+    def ok(self) -> bool:
+        """False if any call timed out waiting for a peer (device sync)."""
+        return int(self.status) == 0
