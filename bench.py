@@ -526,7 +526,7 @@ def main():
         g0_bytes = V * (2 * esz + 4)
         roof = {
             "bound": "fp32", "kernel": dom, "achieved": fl / t_dom / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": fl / t_dom / 1e12 / peak_tf, "traffic": None,
+            "frac": fl / t_dom / 1e12 / peak_tf, "traffic": _ncu_traffic(dom),
             "peak_source": "FP32 FFMA probe measured in this run (sn_fp32_peak_probe); MEASURED_PEAKS.json has no FP32-pipe figure",
             "algorithmic": {"flops_per_voxel_per_kernel": 2 * T, "voxels_per_launch": V, "bytes_per_launch": bytes_dom},
             "hbm": {"achieved": bytes_dom / t_dom / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": bytes_dom / t_dom / 1e9 / hbm_gbs,
@@ -572,6 +572,17 @@ def main():
         # no destroy_process_group(): tearing NCCL down under live CUDA graphs that contain collectives hung the
         # first 2-GPU run after the result line had been printed; every rank leaves once rank 0 is done printing
         os._exit(0)
+
+
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture
+    (profiles/r1b_traffic.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+            d = json.load(f)[kernel]
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def _spec_params(model):

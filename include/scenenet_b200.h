@@ -143,7 +143,7 @@ int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, con
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
  *   G0 = dpred * (1 - pred^2) * [pred > 0];   W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t]
  *   x [B,1,Z,X,Y] float32, pred / dpred in pred_dtype / dpred_dtype, W [T] float64 out.
- *   nnz: DEVICE pointer to the number of non-zero voxels of x as written by sn_grid_prepare, or NULL.
+ *   nnz: DEVICE pointer to the two-word count buffer of x as written by sn_grid_prepare, or NULL.
  *        Voxel grids of point clouds are ~98 % empty: when nnz is given, an occupancy-driven
  *        kernel (cost proportional to the occupied voxels) and the dense stencil are both enqueued and the
  *        count selects ON THE DEVICE which of them does the work (sparse up to 10 % occupancy; no host
@@ -214,7 +214,9 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
  * ====================================================================================== */
 /* Grid preparation, one HBM pass: x (SN_F64 as handed over by the reference's ToTensor, torch_transforms.py:13;
  * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
- * nothing is copied) and *nnz = number of non-zero voxels (device, 8-byte aligned; zeroed by the call).
+ * nothing is copied) and nnz[0] = number of non-zero voxels.  nnz: DEVICE buffer of TWO uint64, 16-byte aligned,
+ * zeroed by the call: [0] the count, [1] a ticket counter the tap-gradient kernels use to let their last CTA
+ * sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward).
  * x and x32 16-byte aligned. */
 int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream);
 /* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */

@@ -162,9 +162,9 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     if (dtype != SN_F32 && dtype != SN_F64 && dtype != SN_U8) return SN_ERR_BAD_ARG;
     if (dtype != SN_F32 && !x32) return SN_ERR_BAD_ARG;
     if (dtype == SN_F32 && x32 && (const void*)x32 != x) return SN_ERR_BAD_ARG;  // float32 grids are used in place
-    if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
+    if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 15)) return SN_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(nnz, 0, sizeof(unsigned long long), s);
+    cudaError_t e = cudaMemsetAsync(nnz, 0, 2 * sizeof(unsigned long long), s);  // [0] count, [1] ticket of the tap-gradient tail
     if (e != cudaSuccess) return sn::cuda_rc(e);
     if (n == 0) return SN_OK;
     if (dtype == SN_F64)

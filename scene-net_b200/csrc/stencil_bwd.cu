@@ -36,7 +36,7 @@ int stencil_tapgrad_generic(const BwdParams& p, int ky, double* W, cudaStream_t 
 int64_t tapgrad_sparse_ws(int B, int Z, int X, int Y, int kz, int kx, int ky);
 int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long long* nnz, unsigned long long nnz_max,
                           int B, int Z, int X, int Y, int kz, int kx, int ky, void* ws, int64_t ws_bytes, int* rows_out,
-                          cudaStream_t stream);
+                          double* W, unsigned long long* ticket, cudaStream_t stream);
 
 // G0 = dpred * (1 - pred^2) * [pred > 0]: 4 voxels per thread, all loads issued before use
 template <typename TP, typename TD>
@@ -206,12 +206,15 @@ extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsign
     if (run_dense && !fast_ky(ky)) return sn::stencil_tapgrad_generic(p, ky, W, s);
     if (!ws) return SN_ERR_WORKSPACE;
     int rows = 0, rows_sparse = 0, TP = (T + 31) & ~31, rc = SN_OK;
+    // with a count buffer from sn_grid_prepare the second word is a ticket counter (zeroed by that call): the CTA
+    // that finishes last sums the partial rows itself; without it a separate kernel does
+    unsigned long long* ticket = (mode == SN_TAPGRAD_AUTO && nnz) ? const_cast<unsigned long long*>(nnz) + 1 : nullptr;
     if (run_sparse) {
-        rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, s);
+        rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, W, ticket, s);
         if (rc) return rc;
     }
     if (run_dense) {
-        p.nnz = gate; p.nnz_max = nnz_max;
+        p.nnz = gate; p.nnz_max = nnz_max; p.W = W; p.ticket = ticket;
         switch (ky) {
             case 3: rc = sn::stencil_bwd_ky3(p, ws, ws_bytes, &rows, &TP, s); break;
             case 5: rc = sn::stencil_bwd_ky5(p, ws, ws_bytes, &rows, &TP, s); break;
@@ -226,6 +229,7 @@ extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsign
     } else {
         rows = rows_sparse;  // ungated sparse run: the reduction reads its rows
     }
+    if (ticket) return SN_OK;  // W was written by the last CTA of whichever kernel ran
     // fixed-order float64 reduction of the partial rows
     sn::reduce_partials_kernel<<<sn::ceil_div(T, 32), dim3(32, 32), 0, s>>>(reinterpret_cast<const double*>(ws), rows, rows_sparse,
                                                                               gate, nnz_max, TP, T, W);

@@ -38,6 +38,8 @@ struct SpParams {
     const float* x;
     const float* g0;
     double* partial;                 // [gridDim.x][TP]
+    double* W;                       // [T]: written by the last CTA when `ticket` is given
+    unsigned long long* ticket;      // device counter zeroed by sn_grid_prepare (NULL: a separate kernel sums the rows)
     const unsigned long long* nnz;   // device; NULL = always run
     unsigned long long nnz_max;      // run iff *nnz <= nnz_max
     int B, Z, X, Y, kz, kx, ky;
@@ -224,6 +226,7 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
         for (int q = 0; q < p.S; ++q) a += sred[(cc * p.S + q) * kSpChunk + tl];
         row[t] = a;
     }
+    if (p.ticket) last_cta_row_sum(p.ticket, p.partial, (int)gridDim.x, p.TP, T, p.W);
 }
 
 // Shared-memory wavefronts one non-zero voxel costs: lanes read G0 box elements at -(dz*zs + dx*WS + dy), and a
@@ -325,14 +328,14 @@ int64_t tapgrad_sparse_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
 // rows_out = partial rows written (0 when the sparse kernel is not applicable)
 int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long long* nnz, unsigned long long nnz_max,
                           int B, int Z, int X, int Y, int kz, int kx, int ky, void* ws, int64_t ws_bytes, int* rows_out,
-                          cudaStream_t stream) {
+                          double* W, unsigned long long* ticket, cudaStream_t stream) {
     SpParams p{};
     size_t smem;
     *rows_out = 0;
     if (!plan_sparse(B, Z, X, Y, kz, kx, ky, p, smem)) return SN_OK;
     const int grid = min(p.ntiles, kNumSMs);
     if ((int64_t)grid * p.TP * 8 > ws_bytes) return SN_ERR_WORKSPACE;
-    p.x = x; p.g0 = g0; p.nnz = nnz; p.nnz_max = nnz_max;
+    p.x = x; p.g0 = g0; p.nnz = nnz; p.nnz_max = nnz_max; p.W = W; p.ticket = ticket;
     p.partial = reinterpret_cast<double*>(ws);
     CUtensorMap xmap, gmap;
     const bool okx = make_grid_tmap(&xmap, x, B, Z, X, Y, kRZ, p.IX, p.IY);

@@ -66,6 +66,8 @@ struct BwdParams {
     // the dense kernel returns at once when nnz != NULL and *nnz <= nnz_max
     const unsigned long long* nnz;
     unsigned long long nnz_max;
+    double* W;                   // [T]: written by the last CTA when `ticket` is given
+    unsigned long long* ticket;  // device counter zeroed by sn_grid_prepare (NULL: a separate kernel sums the rows)
 };
 
 // G0 = dL/ds = dpred * (1 - pred^2) * [pred > 0], evaluated in float64 and rounded once: the parameter
@@ -101,6 +103,36 @@ __device__ __forceinline__ double tanh_pos_f64(double s) {
     const int k = (int)kf;
     const double e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // p * 2^k, k in [0, 58]
     return 1.0 - 2.0 / (e + 1.0);
+}
+
+// Tail of the tap-gradient kernels: the CTA that draws the last ticket sums the partial rows of all CTAs in row order
+// (fixed order: deterministic) into W — no separate reduction launch.  `ticket` is zeroed once per step by
+// sn_grid_prepare; `total` = number of CTAs that take a ticket.  Call with all threads of the CTA.
+__device__ __forceinline__ void last_cta_row_sum(unsigned long long* ticket, const double* __restrict__ partial, int rows, int TP,
+                                                 int T, double* __restrict__ W, int total = -1) {
+    __shared__ int s_last;
+    __threadfence();  // this CTA's row is visible device-wide before its ticket is drawn
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+        s_last = atomicAdd(ticket, 1ULL) == (unsigned long long)((total < 0 ? rows : total) - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int t = tid; t < T; t += nthreads) {
+        double a = 0.0;
+        int r = 0;
+        for (; r + 8 <= rows; r += 8) {  // 8 independent loads in flight, summed in row order
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldcg(partial + (size_t)(r + i) * TP + t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a += v[i];
+        }
+        for (; r < rows; ++r) a += __ldcg(partial + (size_t)r * TP + t);
+        W[t] = a;
+    }
+    if (tid == 0) *ticket = 0ULL;  // ready for another backward on the same count buffer (retain_graph, re-runs)
 }
 
 // tile geometry shared by host and device

@@ -176,7 +176,7 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
 
 def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
-    (x itself for float32 input), nnz a 1-element int64 device tensor with the number of non-zero voxels: the
+    (x itself for float32 input), nnz a 2-element int64 device tensor ([0] = number of non-zero voxels): the
     forward and the backward use it ON THE DEVICE to pick the occupancy-driven kernels for sparse grids.
     stream: run the pass on this (side) stream after everything enqueued so far on the current one; the outputs
     are allocated on the current stream and the caller joins the streams (`current.wait_stream(stream)`)."""
@@ -190,8 +190,8 @@ def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
         x = x.clone()
     x32 = x if x.dtype == torch.float32 else torch.empty(x.shape, dtype=torch.float32, device=x.device)
     if x.numel() == 0:
-        return x32, torch.zeros(1, dtype=torch.int64, device=x.device)
-    nnz = torch.empty(1, dtype=torch.int64, device=x.device)
+        return x32, torch.zeros(2, dtype=torch.int64, device=x.device)
+    nnz = torch.empty(2, dtype=torch.int64, device=x.device)  # [0] non-zero count, [1] ticket counter of the backward
     dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
     with torch.cuda.device(x.device):
         if stream is not None:

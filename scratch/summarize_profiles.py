@@ -1,0 +1,45 @@
+"""gpurun_out/ ncu outputs -> small tracked summaries under profiles/ (run from the repo root)"""
+import collections, csv, os, subprocess, sys
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
+out = "profiles"
+# 1. launch list of the bench command -> copy (kernels of this library only) + per-kernel summary
+src = f"gpurun_out/{tag}_launches_bench.csv"
+rows = list(csv.reader(open(src)))
+for i, r in enumerate(rows):
+    if "Kernel Name" in r:
+        hdr, start = r, i + 1
+        break
+kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+keep = [hdr] + [r for r in rows[start:] if len(r) > mv and "sn::" in r[kn]]
+with open(f"{out}/{tag}_launches_bench.csv", "w", newline="") as f:
+    csv.writer(f).writerows(keep)
+agg = collections.OrderedDict()
+for r in keep[1:]:
+    agg.setdefault(r[kn], []).append(float(r[mv].replace(",", "")) / 1000.0)
+with open(f"{out}/{tag}_launch_summary.csv", "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow(["kernel", "launches", "avg_us", "min_us", "max_us", "note: ncu = cold cache, serialised; forced-mode and device-gated launches of the same kernel are mixed in bench.py"])
+    for k, v in agg.items():
+        w.writerow([k[:110], len(v), f"{sum(v)/len(v):.1f}", f"{min(v):.1f}", f"{max(v):.1f}"])
+# 2. ncu --set full captures -> selected raw metrics
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active"]
+for rep, name in [(f"gpurun_out/prof_r1_step.ncu-rep", f"{tag}_ncu_step_kernels.csv"), ("gpurun_out/prof_fsparse_r1.ncu-rep", f"{tag}_ncu_fwd_sparse.csv"),
+                  ("gpurun_out/prof_bin_r1.ncu-rep", f"{tag}_ncu_vox_bin.csv")]:
+    if not os.path.exists(rep):
+        continue
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, units = rr[0], rr[1]
+    cols = [h.index("Kernel Name")] + [h.index(m) for m in WANT if m in h] + [i for i, c in enumerate(h) if "issue_stalled" in c and c.endswith("_per_issue_active.ratio")]
+    with open(f"{out}/{name}", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [r[cols[0]][:60] for r in rr[2:]])
+        for c in cols[1:]:
+            w.writerow([h[c], units[c]] + [r[c] for r in rr[2:]])
+print("ok", os.listdir(out))

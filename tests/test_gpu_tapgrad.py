@@ -76,13 +76,15 @@ def test_device_side_selection(density, expect_sparse):
     for dt in (torch.float64, torch.float32, torch.uint8):
         xin = (x != 0).to(dt) if dt == torch.uint8 else x.to(dt)
         x32, nnz = ops.prepare(xin)
-        assert int(nnz) == int((xin != 0).sum())
+        assert int(nnz[0]) == int((xin != 0).sum())
         assert x32.dtype == torch.float32 and torch.equal(x32, xin.to(torch.float32))
         Wa = ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_AUTO)
         We = ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_SPARSE if expect_sparse else SN_TAPGRAD_DENSE)
         Wo = ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_DENSE if expect_sparse else SN_TAPGRAD_SPARSE)
         assert torch.equal(Wa, We)
         assert torch.allclose(Wa, Wo, rtol=1e-4, atol=1e-4 * float(Wo.abs().max()))
+        # the same count buffer serves a second backward (the last CTA resets its ticket)
+        assert torch.equal(ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_AUTO), We)
     # no count -> dense
     assert torch.equal(ops.tapgrad(x, g0, ks), ops.tapgrad(x, g0, ks, mode=SN_TAPGRAD_DENSE))
 
