@@ -162,3 +162,20 @@ def test_live_reference_random_params():
                 assert grads[n] is None
             else:
                 assert abs(grads[n] - float(p.grad)) <= 1e-5 * abs(float(p.grad)) + 1e-10, (n, grads[n], float(p.grad))
+
+
+def test_fused_criterion_weight_table_matches_oracle_weights():
+    """host logic of the fused criterion: the 10-entry table the kernels look up equals what the oracle's (= the
+    reference's) per-voxel weight computation yields before the division by the mean (CPU only, no kernel call)"""
+    import torch
+    import scenenet_b200 as sb
+    from oracle import model_oracle as mo
+    crit = sb.WeightedMSE(hist=(mo.HIST_FREQS, mo.HIST_RANGES), weight_alpha=1, weight_epsilon=0.1)
+    ranges, w_raw = crit._weight_table()
+    assert len(ranges) == len(w_raw) == 10
+    y = torch.tensor([0.0, 1.0, 0.26, 0.74, 0.5], dtype=torch.float64)
+    w = mo.weight_target(y)                       # normalised by its mean
+    bins = [int(torch.argmin(torch.abs(v - torch.tensor(ranges, dtype=torch.float64)))) for v in y]
+    raw = torch.tensor([w_raw[b] for b in bins], dtype=torch.float32)
+    assert torch.allclose(raw / raw.mean(), w.to(torch.float32), rtol=1e-6, atol=0)
+    assert abs(w_raw[0] - 0.1) < 1e-7 and abs(w_raw[9] - 0.5304348) < 1e-6   # SURVEY App. C probe values
