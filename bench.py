@@ -420,7 +420,7 @@ def main():
     graphs = None
     if not args.eager:
         # one captured step per input set: static addresses, no staging copies inside the timed region
-        graphs = [GraphedStep(model, x, dpred=dp, post_backward=post) for x, dp in pool]
+        graphs = [GraphedStep(model, x, dpred=dp, post_backward=post, specialize=True) for x, dp in pool]
 
     def step(i):
         if graphs is None:
@@ -456,9 +456,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms)
     value = B_PER_GPU * world * args.steps / (total_ms * 1e-3)
-    # synth, prepare (cast + non-zero count), fwd stencil, g0, occupancy-driven tap gradient, dense tap gradient
-    # (returns at once on sparse grids), row reduction, param_grads
-    kernels_per_step = 8
+    # synth, prepare (cast + non-zero count), forward, g0, tap gradient (its last CTA sums the rows), param_grads
+    # [+ the peer-memory all-reduce kernel]; specialised capture: no gated-out launches
+    kernels_per_step = 6 + (1 if (world > 1 and callable(model.grad_sync_group)) else 0)
     if graphs is not None:
         launches = kernels_per_step * args.steps  # replayed graph nodes: the library's host-side counter does not see them
 
@@ -555,7 +555,7 @@ def main():
             g = torch.Generator(device=device).manual_seed(4321 + s_)
             ys.append((torch.rand((B_PER_GPU, 1, *GRID), generator=g, device=device) < 3e-4).to(io_dtype))
         tgraphs = [GraphedStep(model, pool[s_][0], loss_fn=(lambda pred, y=ys[s_]: crit(pred, y, model.get_cvx_coefficients(),
-                                                                                         model.get_geneo_params())))
+                                                                                         model.get_geneo_params())), specialize=True)
                    for s_ in range(n_sets)]
         for i in range(args.warmup):
             tgraphs[i % n_sets].replay()

@@ -147,14 +147,20 @@ int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, con
  *        Voxel grids of point clouds are ~98 % empty: when nnz is given, an occupancy-driven
  *        kernel (cost proportional to the occupied voxels) and the dense stencil are both enqueued and the
  *        count selects ON THE DEVICE which of them does the work (sparse up to 10 % occupancy; no host
- *        synchronisation).  With NULL the dense stencil always runs.  Same W either way, up to float32
+ *        synchronisation).  With NULL the dense stencil always runs.  mode: SN_PATH_AUTO / _DENSE / _SPARSE as for
+ *        sn_scenenet_fwd (forced modes enqueue one kernel only).  Same W either way, up to float32
  *        summation order (the occupancy-driven kernel only skips terms that are exactly zero).
  *   ws: workspace of at least sn_scenenet_bwd_workspace_bytes(...) bytes, 16-byte aligned.
  * Deterministic: fixed partition, fixed-order float64 reduction, no floating-point atomics. */
 int64_t sn_scenenet_bwd_workspace_bytes(int B, int Z, int X, int Y, int kz, int kx, int ky);
-int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, const void* pred, int pred_dtype,
+int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, int mode, const void* pred, int pred_dtype,
                     const void* dpred, int dpred_dtype, int B, int Z, int X, int Y, int kz, int kx, int ky,
                     double* W, void* ws, int64_t ws_bytes, void* stream);
+/* The selection rule of SN_PATH_AUTO for a host that already knows the occupancy (a step captured once for replay on
+ * grids of one kind can then enqueue only the kernel that will work; both kernels are correct at ANY occupancy, the
+ * choice only affects speed).  which: 0 = forward, 1 = tap gradient.  Returns SN_PATH_DENSE / SN_PATH_SPARSE. */
+int sn_select_path(int which, int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
+int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
 
 /* The two passes of sn_scenenet_bwd, callable on their own (measurement, fused criterions that
  * produce G0 themselves):  G0 [n] float32 = dpred * (1 - pred^2) * [pred > 0] evaluated in float64 and

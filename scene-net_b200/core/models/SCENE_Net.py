@@ -39,7 +39,7 @@ class _ObserverFunction(torch.autograd.Function):
     """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
 
     @staticmethod
-    def forward(ctx, x, spec, write_last, grad_scale, sync_group, *params):
+    def forward(ctx, x, spec, write_last, grad_scale, sync_group, path_modes, *params):
         # kernel synthesis (one latency-bound CTA) and grid preparation (HBM-bound) are independent: the preparation
         # runs on a side stream (a parallel branch when the step is captured in a CUDA graph)
         cur = torch.cuda.current_stream(x.device)
@@ -48,7 +48,9 @@ class _ObserverFunction(torch.autograd.Function):
         K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         cur.wait_stream(side)
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
-        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz)
+        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz,
+                                mode=path_modes[0])
+        ctx.bwd_mode = path_modes[1]
         ctx.spec = spec
         ctx.grad_scale = grad_scale
         ctx.sync_group = sync_group
@@ -58,7 +60,7 @@ class _ObserverFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpred):
         x32, pred, K, lam, snap, nnz = ctx.saved_tensors
-        W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size, nnz)
+        W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size, nnz, mode=ctx.bwd_mode)
         d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
         if ctx.sync_group is not None:
             # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
@@ -69,8 +71,8 @@ class _ObserverFunction(torch.autograd.Function):
                 import torch.distributed as dist
                 dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
         unused = ctx.spec.unused
-        grads = [d[i] if (ctx.needs_input_grad[i + 5] and i not in unused) else None for i in range(d.numel())]
-        return (None, None, None, None, None, *grads)
+        grads = [d[i] if (ctx.needs_input_grad[i + 6] and i not in unused) else None for i in range(d.numel())]
+        return (None, None, None, None, None, None, *grads)
 
 
 def _apex_int(layer) -> int:
@@ -169,6 +171,10 @@ class _SceneNetBase(nn.Module):
         #: None = no collective (single GPU, or DDP/Lightning does it); True / a process group = all-reduce (SUM) the
         #: flat gradient payload inside backward (use with grad_scale = 1/world for the DDP mean)
         self.grad_sync_group = None
+        #: (forward, backward) kernel choice: 0 = decided on the device from the grid's non-zero count (both kernels are
+        #: enqueued, one returns at once), 1 = dense stencil, 2 = occupancy-driven kernel.  Both are correct at any
+        #: occupancy; a step captured for replay can pin the choice (graphs.GraphedStep(specialize=True))
+        self.path_modes = (0, 0)
         if plot:
             print(f"Total Number of train params = {self.get_num_total_params()}")
 
@@ -235,7 +241,7 @@ class _SceneNetBase(nn.Module):
         if x.device != params[0].device:
             raise RuntimeError(f"input on {x.device} but model on {params[0].device}")
         # write_last=True reproduces the side effect of SCENE_Net.py:333 (last lambda <- 1 - sum(others)), in place
-        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, *params)
+        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, tuple(self.path_modes), *params)
 
 
 class SCENE_Net(_SceneNetBase):

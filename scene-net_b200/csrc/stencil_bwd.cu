@@ -121,6 +121,8 @@ static int launch_g0(const BwdParams& p, long long n, float* g0, cudaStream_t st
 
 }  // namespace sn
 
+extern "C" int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);  // stencil_fwd.cu
+
 static int64_t tapgrad_ws_dense(int B, int Z, int X, int Y, int kz, int kx, int ky) {
     switch (ky) {
         case 3: return sn::stencil_bwd_ws_ky3(B, Z, X, Y, kz, kx);
@@ -208,7 +210,7 @@ extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsign
     int rows = 0, rows_sparse = 0, TP = (T + 31) & ~31, rc = SN_OK;
     // with a count buffer from sn_grid_prepare the second word is a ticket counter (zeroed by that call): the CTA
     // that finishes last sums the partial rows itself; without it a separate kernel does
-    unsigned long long* ticket = (mode == SN_TAPGRAD_AUTO && nnz) ? const_cast<unsigned long long*>(nnz) + 1 : nullptr;
+    unsigned long long* ticket = nnz ? const_cast<unsigned long long*>(nnz) + 1 : nullptr;
     if (run_sparse) {
         rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, W, ticket, s);
         if (rc) return rc;
@@ -237,7 +239,7 @@ extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsign
     return SN_OK;
 }
 
-extern "C" int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, const void* pred, int pred_dtype,
+extern "C" int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, int mode, const void* pred, int pred_dtype,
                                const void* dpred, int dpred_dtype, int B, int Z, int X, int Y, int kz, int kx, int ky,
                                double* W, void* ws, int64_t ws_bytes, void* stream) {
     if (!x || !pred || !dpred || !W || !ws) return SN_ERR_BAD_ARG;
@@ -248,6 +250,20 @@ extern "C" int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, co
     float* g0 = reinterpret_cast<float*>(ws);
     int rc = sn_scenenet_g0(pred, pred_dtype, dpred, dpred_dtype, (int64_t)B * Z * X * Y, g0, stream);
     if (rc) return rc;
-    return sn_scenenet_tapgrad(x, g0, nnz, SN_TAPGRAD_AUTO, B, Z, X, Y, kz, kx, ky, W, reinterpret_cast<char*>(ws) + gb,
+    return sn_scenenet_tapgrad(x, g0, nnz, mode, B, Z, X, Y, kz, kx, ky, W, reinterpret_cast<char*>(ws) + gb,
                                ws_bytes - gb, stream);
+}
+
+// the selection rule of the AUTO modes, for hosts that know the occupancy (e.g. when a step is captured for replay on
+// grids of one kind): which = 0 forward, 1 tap gradient.  Returns SN_PATH_DENSE or SN_PATH_SPARSE.
+extern "C" int sn_select_path(int which, int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1 || nnz < 0) return SN_ERR_BAD_ARG;
+    const long long nvox = (long long)B * Z * X * Y;
+    if (which == 1) {
+        const bool ok = sn::tapgrad_sparse_ws(B, Z, X, Y, kz, kx, ky) > 0;
+        if (ok && !fast_ky(ky)) return SN_PATH_SPARSE;
+        return (ok && (unsigned long long)nnz <= sparse_nnz_max(nvox)) ? SN_PATH_SPARSE : SN_PATH_DENSE;
+    }
+    if (which == 0) return sn_select_fwd_path(nnz, B, Z, X, Y, kz, kx, ky);
+    return SN_ERR_BAD_ARG;
 }

@@ -84,3 +84,10 @@ extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, in
     }
     return rc;
 }
+
+extern "C" int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    const bool ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
+    const bool fast = ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15;
+    if (ok && !fast) return SN_PATH_SPARSE;
+    return (ok && (unsigned long long)nnz <= fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky)) ? SN_PATH_SPARSE : SN_PATH_DENSE;
+}

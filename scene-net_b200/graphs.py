@@ -4,9 +4,9 @@ At B200 speed one fwd+bwd of a 32-grid batch is ~250 us of GPU work in 7 kernels
 than what Python + autograd spend launching them: the eager module path is host-bound.  A step
 on static buffers is therefore captured once (our kernels are launched on torch's current
 stream, so `torch.cuda.graph` records them like any other) and replayed with one
-cudaGraphLaunch.  The graph contains, in order: [H2D copy of x] -> synthesis -> cast ->
-stencil/observer forward -> [criterion] -> G0 -> tap-gradient -> reduction -> parameter
-Jacobian -> [NCCL all-reduce] -> [D2H copy of the gradients].
+cudaGraphLaunch.  The graph contains: [H2D copy of x] -> (kernel synthesis || grid preparation) ->
+observer forward -> [criterion] -> G0 -> tap gradient (rows summed by its last CTA) -> parameter
+Jacobian -> [gradient all-reduce] -> [D2H copy of the gradients].
 """
 from __future__ import annotations
 
@@ -28,16 +28,26 @@ class GraphedStep:
     grads_host: optional pinned host float32 tensor [n_trainable]; when given every replay ends with the
               D2H copy of the flat gradient vector into it
     post_backward: optional callable run (and captured) after backward, e.g. the gradient all-reduce
+    specialize: read the occupancy of `x` once before capture and enqueue only the kernels the device-side
+              selection would pick for such grids (dense stencil or occupancy-driven kernel); replays on
+              other data stay correct
     """
 
     def __init__(self, model: torch.nn.Module, x: torch.Tensor, dpred: Optional[torch.Tensor] = None,
                  loss_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, x_host: Optional[torch.Tensor] = None,
                  grads_host: Optional[torch.Tensor] = None, post_backward: Optional[Callable[[], None]] = None,
-                 warmup: int = 3):
+                 warmup: int = 3, specialize: bool = False):
         if (dpred is None) == (loss_fn is None):
             raise ValueError("give exactly one of dpred / loss_fn")
         self.model, self.x, self.dpred, self.loss_fn = model, x, dpred, loss_fn
         self.x_host, self.grads_host, self.post_backward = x_host, grads_host, post_backward
+        # specialize: read the occupancy of `x` once (host sync, before capture) and enqueue only the kernels the
+        # device-side selection would pick for grids like it — no gated-out launches in the graph.  Both kernel
+        # families are correct at any occupancy, so replaying on other data stays correct (only slower).
+        self.path_modes = None
+        if specialize and hasattr(model, "path_modes") and x.numel() and (x_host is None):
+            from . import ops
+            self.path_modes = ops.select_paths(x, model._spec_and_params()[0].kernel_size)
         self.params: Sequence[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.pred = None
         self.loss = None
@@ -58,7 +68,14 @@ class GraphedStep:
     def _step(self):
         if self.x_host is not None:
             self.x.copy_(self.x_host, non_blocking=True)
-        self.pred = self.model(self.x)
+        if self.path_modes is not None:
+            saved, self.model.path_modes = self.model.path_modes, self.path_modes
+            try:
+                self.pred = self.model(self.x)
+            finally:
+                self.model.path_modes = saved
+        else:
+            self.pred = self.model(self.x)
         # torch.autograd.grad instead of .backward(): no AccumulateGrad nodes take part, so parameters that
         # were already used eagerly (their AccumulateGrad lives on the legacy stream) cannot break the capture
         if self.loss_fn is not None:

@@ -238,7 +238,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 
 def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, kernel_size,
-                 nnz: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 nnz: Optional[torch.Tensor] = None, mode: int = 0) -> torch.Tensor:
     """tap gradient W [kz,kx,ky] float64.  nnz (from `prepare`) enables the device-side choice of the
     occupancy-driven kernel."""
     B, Z, X, Y = _grid_dims(x32)
@@ -258,10 +258,19 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
     nbytes = int(lib.sn_scenenet_bwd_workspace_bytes(B, Z, X, Y, kz, kx, ky))
     ws = _workspace(nbytes, x32.device)
     with torch.cuda.device(x32.device):
-        check(lib.sn_scenenet_bwd(x32.data_ptr(), _ptr(nnz), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
+        check(lib.sn_scenenet_bwd(x32.data_ptr(), _ptr(nnz), int(mode), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
                                   B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
               "sn_scenenet_bwd")
     return W
+
+
+def select_paths(x: torch.Tensor, kernel_size) -> tuple:
+    """(forward mode, backward mode) the device-side selection would pick for grids like `x` — reads the non-zero count
+    on the host (one synchronisation; meant for capture time, see graphs.GraphedStep)."""
+    B, Z, X, Y = _grid_dims(x)
+    kz, kx, ky = (int(v) for v in kernel_size)
+    n = int(torch.count_nonzero(x))
+    return (int(lib.sn_select_path(0, n, B, Z, X, Y, kz, kx, ky)), int(lib.sn_select_path(1, n, B, Z, X, Y, kz, kx, ky)))
 
 
 def g0(pred: torch.Tensor, dpred: torch.Tensor) -> torch.Tensor:

@@ -379,6 +379,10 @@ def test_graphed_step_matches_eager():
     xs = torch.zeros_like(x)
     gs = GraphedStep(mg, xs, dpred=dp)
     xs.copy_(x)
+    # a capture specialised on the grids' occupancy (only the selected kernels are enqueued) gives the same bits
+    mg2 = _make_model(mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, (9, 5, 5))
+    gs2 = GraphedStep(mg2, x.clone(), dpred=dp, specialize=True)
+    assert gs2.path_modes is not None and all(m in (1, 2) for m in gs2.path_modes)
     outs = []
     for _ in range(2):
         out = gs.replay()
@@ -393,3 +397,8 @@ def test_graphed_step_matches_eager():
         assert torch.equal(out, pred.detach())
         for g, r in zip(grads, ref_g):
             assert torch.equal(g, r)
+    out2 = gs2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, pred.detach())
+    for g, r in zip([p.grad for p in gs2.params], ref_g):
+        assert torch.equal(g, r)
