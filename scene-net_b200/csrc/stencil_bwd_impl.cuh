@@ -158,7 +158,10 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
             if (dzl < cs) row[((ch * C + dzl) * p.kx + dx) * KY + dy] = s;
         }
     }
-    if (p.ticket) last_cta_row_sum(p.ticket, p.partial, (int)gridDim.x, p.TP, p.kz * p.kx * KY, p.W, (int)(gridDim.x * gridDim.y));
+    if (p.ticket) {
+        __syncthreads();  // sred is reused as scratch
+        last_cta_row_sum(p.ticket, p.partial, (int)gridDim.x, p.TP, p.kz * p.kx * KY, p.W, sred, (int)(gridDim.x * gridDim.y));
+    }
 }
 
 struct BwdPlan {

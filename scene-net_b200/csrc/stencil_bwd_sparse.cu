@@ -226,7 +226,10 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
         for (int q = 0; q < p.S; ++q) a += sred[(cc * p.S + q) * kSpChunk + tl];
         row[t] = a;
     }
-    if (p.ticket) last_cta_row_sum(p.ticket, p.partial, (int)gridDim.x, p.TP, T, p.W);
+    if (p.ticket) {
+        __syncthreads();  // sred is reused as scratch
+        last_cta_row_sum(p.ticket, p.partial, (int)gridDim.x, p.TP, T, p.W, sred);
+    }
 }
 
 // Shared-memory wavefronts one non-zero voxel costs: lanes read G0 box elements at -(dz*zs + dx*WS + dy), and a

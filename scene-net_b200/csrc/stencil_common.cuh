@@ -109,28 +109,47 @@ __device__ __forceinline__ double tanh_pos_f64(double s) {
 // (fixed order: deterministic) into W — no separate reduction launch.  `ticket` is zeroed once per step by
 // sn_grid_prepare; `total` = number of CTAs that take a ticket.  Call with all threads of the CTA.
 __device__ __forceinline__ void last_cta_row_sum(unsigned long long* ticket, const double* __restrict__ partial, int rows, int TP,
-                                                 int T, double* __restrict__ W, int total = -1) {
+                                                 int T, double* __restrict__ W, double* __restrict__ scratch, int total = -1) {
+    // scratch: shared memory of this CTA, at least min(nwarps, kRowSumGroups) * 256 doubles (the tile stages are dead)
+    constexpr int kRowSumGroups = 16;
     __shared__ int s_last;
     __threadfence();  // this CTA's row is visible device-wide before its ticket is drawn
     __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0)
-        s_last = atomicAdd(ticket, 1ULL) == (unsigned long long)((total < 0 ? rows : total) - 1) ? 1 : 0;
+    const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) s_last = atomicAdd(ticket, 1ULL) == (unsigned long long)((total < 0 ? rows : total) - 1) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int t = tid; t < T; t += nthreads) {
-        double a = 0.0;
-        int r = 0;
-        for (; r + 8 <= rows; r += 8) {  // 8 independent loads in flight, summed in row order
-            double v[8];
+    // warp g sums rows g, g + G, ... (lanes <-> taps, 8 loads in flight per lane), then the G group sums are added in
+    // group order: a fixed order whatever the timing (a single pass of T threads over all rows took ~7 us)
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    const int G = nwarps < kRowSumGroups ? nwarps : kRowSumGroups;
+    for (int t0 = 0; t0 < T; t0 += 256) {  // 256 taps per sweep (scratch [G][256])
+        if (warp < G) {
+            for (int tt = lane; tt < 256; tt += 32) {
+                const int t = t0 + tt;
+                double a = 0.0;
+                if (t < T) {
+                    int r = warp;
+                    for (; r + 7 * G < rows; r += 8 * G) {
+                        double v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __ldcg(partial + (size_t)(r + i) * TP + t);
+                        for (int i = 0; i < 8; ++i) v[i] = __ldcg(partial + (size_t)(r + i * G) * TP + t);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a += v[i];
+                        for (int i = 0; i < 8; ++i) a += v[i];
+                    }
+                    for (; r < rows; r += G) a += __ldcg(partial + (size_t)r * TP + t);
+                }
+                scratch[warp * 256 + tt] = a;
+            }
         }
-        for (; r < rows; ++r) a += __ldcg(partial + (size_t)r * TP + t);
-        W[t] = a;
+        __syncthreads();
+        for (int tt = tid; tt < 256 && t0 + tt < T; tt += nthreads) {
+            double a = 0.0;
+            for (int g = 0; g < G; ++g) a += scratch[g * 256 + tt];
+            W[t0 + tt] = a;
+        }
+        __syncthreads();
     }
     if (tid == 0) *ticket = 0ULL;  // ready for another backward on the same count buffer (retain_graph, re-runs)
 }
