@@ -50,10 +50,23 @@ __device__ __forceinline__ void add_count(unsigned cnt, unsigned long long* nnz)
 
 __global__ void __launch_bounds__(256) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
                                                           unsigned long long* nnz) {
+    // 4 x 16-byte loads in flight per thread (one per step left the pass at 0.73 of the HBM copy rate)
     const long long n2 = n >> 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned cnt = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const double2*>(in)[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 o = make_float2((float)v[u].x, (float)v[u].y);
+            reinterpret_cast<float2*>(out)[i + u * stride] = o;
+            cnt += (o.x != 0.f) + (o.y != 0.f);
+        }
+    }
+    for (; i < n2; i += stride) {
         const double2 v = reinterpret_cast<const double2*>(in)[i];
         const float2 o = make_float2((float)v.x, (float)v.y);
         reinterpret_cast<float2*>(out)[i] = o;
