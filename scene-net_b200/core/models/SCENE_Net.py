@@ -39,14 +39,18 @@ class _ObserverFunction(torch.autograd.Function):
     """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
 
     @staticmethod
-    def forward(ctx, x, spec, write_last, grad_scale, sync_group, path_modes, *params):
+    def forward(ctx, x, spec, write_last, grad_scale, sync_group, path_modes, prepared, *params):
         # kernel synthesis (one latency-bound CTA) and grid preparation (HBM-bound) are independent: the preparation
         # runs on a side stream (a parallel branch when the step is captured in a CUDA graph)
-        cur = torch.cuda.current_stream(x.device)
-        side = _side_stream(x.device)
-        x32, nnz = ops.prepare(x.detach(), stream=side)  # buffers belong to the current stream, the pass runs on `side`
-        K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
-        cur.wait_stream(side)
+        if prepared is not None:  # several observers on the same grids (SCENENetQuantile): one preparation pass for all
+            x32, nnz = prepared
+            K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
+        else:
+            cur = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            x32, nnz = ops.prepare(x.detach(), stream=side)  # buffers belong to the current stream, the pass runs on `side`
+            K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
+            cur.wait_stream(side)
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz,
                                 mode=path_modes[0])
@@ -71,8 +75,8 @@ class _ObserverFunction(torch.autograd.Function):
                 import torch.distributed as dist
                 dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
         unused = ctx.spec.unused
-        grads = [d[i] if (ctx.needs_input_grad[i + 6] and i not in unused) else None for i in range(d.numel())]
-        return (None, None, None, None, None, None, *grads)
+        grads = [d[i] if (ctx.needs_input_grad[i + 7] and i not in unused) else None for i in range(d.numel())]
+        return (None, None, None, None, None, None, None, *grads)
 
 
 def _apex_int(layer) -> int:
@@ -233,7 +237,9 @@ class _SceneNetBase(nn.Module):
                                 unused=frozenset(unused))
         return spec, params
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, _prepared=None) -> torch.Tensor:
+        """same signature as the reference; `_prepared` (internal) = the result of ops.prepare(x) shared between
+        several observers that read the same grids"""
         spec, params = self._spec_and_params()
         if not params[0].is_cuda:
             raise RuntimeError("scenenet_b200: the model lives on the CPU; move it with .cuda() — the hot path is "
@@ -241,7 +247,8 @@ class _SceneNetBase(nn.Module):
         if x.device != params[0].device:
             raise RuntimeError(f"input on {x.device} but model on {params[0].device}")
         # write_last=True reproduces the side effect of SCENE_Net.py:333 (last lambda <- 1 - sum(others)), in place
-        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, tuple(self.path_modes), *params)
+        return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, tuple(self.path_modes),
+                                       _prepared, *params)
 
 
 class SCENE_Net(_SceneNetBase):
@@ -296,7 +303,10 @@ class SCENENetQuantile(nn.Module):
         return [scnet.get_geneo_params() for scnet in self.scnets]
 
     def forward(self, x: torch.Tensor):
-        return torch.cat([net(x).to(torch.float32) for net in self.scnets], dim=1)
+        # SCENE_Net.py:409-415: every quantile's observer reads the same grids — the float32 copy and the non-zero
+        # count are produced once and shared (the observers then differ only in their 13 scalars)
+        prepared = ops.prepare(x.detach()) if x.is_cuda else None
+        return torch.cat([net(x, _prepared=prepared).to(torch.float32) for net in self.scnets], dim=1)
 
 
 class SCENE_Net_Class(nn.Module):

@@ -402,3 +402,24 @@ def test_graphed_step_matches_eager():
     assert torch.equal(out2, pred.detach())
     for g, r in zip([p.grad for p in gs2.params], ref_g):
         assert torch.equal(g, r)
+
+
+def test_quantile_model_shares_the_grid_preparation():
+    """SCENENetQuantile: one observer per quantile on the same grids; outputs and gradients equal those of the
+    observers run on their own"""
+    sb = _sb()
+    torch.manual_seed(3)
+    qm = sb.SCENENetQuantile({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), device=torch.device(DEV))
+    x, _ = mo.synthetic_grids(2, (32, 32, 32), seed=21)
+    x = x.to(DEV)
+    out = qm(x)
+    assert out.shape == (2, 3, 32, 32, 32) and out.dtype == torch.float32
+    singles = [net(x).to(torch.float32) for net in qm.scnets]
+    assert torch.equal(out, torch.cat(singles, dim=1))
+    out.sum().backward()
+    g_shared = [p.grad.clone() for p in qm.parameters() if p.grad is not None]
+    for p in qm.parameters():
+        p.grad = None
+    torch.cat([net(x).to(torch.float32) for net in qm.scnets], dim=1).sum().backward()
+    g_single = [p.grad for p in qm.parameters() if p.grad is not None]
+    assert len(g_shared) == len(g_single) > 0 and all(torch.equal(a, b) for a, b in zip(g_shared, g_single))
