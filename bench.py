@@ -537,6 +537,19 @@ def main():
     xh = [torch.empty(pool[0][0].shape, dtype=io_dtype).pin_memory() for _ in range(2)]
     for j, h in enumerate(xh):
         h.copy_(pool[j][0])
+    # host->device bandwidth of this box for one batch from pinned memory: the ceiling of the float64 e2e figure
+    xd_probe = torch.empty_like(pool[0][0])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xd_probe.copy_(xh[0], non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    ev0.record()
+    for _ in range(5):
+        xd_probe.copy_(xh[0], non_blocking=True)
+    ev1.record()
+    ev1.synchronize()
+    h2d_gbps = 5 * xh[0].numel() * xh[0].element_size() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del xd_probe
     e2e_value, h2d = e2e_measure(xh, [pool[0][1], pool[1][1]])
     d2h = gh.numel() * gh.element_size()
     # the same step fed with byte occupancy grids (what ToFullDense produces; module extension): 8x fewer PCIe bytes
@@ -686,6 +699,9 @@ def main():
                        "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "uint8_occupancy_input": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8},
+                    "h2d_GBps_measured": h2d_gbps, "pcie_bound": B_PER_GPU * world / (h2d / (h2d_gbps * 1e9)),
+                    "pcie_note": "pcie_bound = grids/s at which the H2D copy of x alone saturates the measured host->device rate "
+                                 "(all ranks copying at once)",
                     "note": "x (module-boundary dtype) from pinned host memory every step, double-buffered on a copy stream; "
                             "dL/dpred resident on the device (config 2(i)); gradients copied back and read by the host every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "training_step": train_value, "voxelize": vox, "grad_sync_ok": grad_sync_ok,
