@@ -46,7 +46,7 @@ class _ObserverFunction(torch.autograd.Function):
             x32, nnz = prepared
             K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         else:
-            cur = torch.cuda.current_stream(x.device)
+            cur = ops.current_stream_obj(x.device)
             side = _side_stream(x.device)
             x32, nnz = ops.prepare(x.detach(), stream=side)  # buffers belong to the current stream, the pass runs on `side`
             K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
@@ -96,6 +96,10 @@ def _apex_int(layer) -> int:
 ###############################################################
 
 class GENEO_Layer(nn.Module):
+
+    @property
+    def has_apex(self) -> bool:
+        return 'apex' in self.geneo_params
 
     def __init__(self, geneo_class: GENEO_kernel_torch, kernel_size: tuple = None, smart=False):
         super(GENEO_Layer, self).__init__()
@@ -213,8 +217,22 @@ class _SceneNetBase(nn.Module):
 
     # ---- the hot path -------------------------------------------------------------------
     def _spec_and_params(self):
+        """(ObserverSpec, parameter list).  The spec only depends on the module structure, int(apex) of the cone layers and
+        which lambda is last: it is cached on those (building it was ~40 us of host time per forward)."""
         names = list(self.geneos.keys())
         layers = [self.geneos[n] for n in names]
+        key = (len(names), self.last_lambda, tuple(tuple(l.kernel_size) for l in layers),
+               tuple(_apex_int(l) if l.has_apex else -1 for l in layers))
+        cached = self.__dict__.get('_spec_cache')
+        if cached is not None and cached[0] == key:
+            params = [l.geneo_params[p] for l in layers for p in l.geneo_class.abi_params]
+            params.extend(self.lambdas_dict[f'lambda_{n}'] for n in names)
+            return cached[1], params
+        spec, params = self._build_spec_and_params(names, layers)
+        self.__dict__['_spec_cache'] = (key, spec)
+        return spec, params
+
+    def _build_spec_and_params(self, names, layers):
         ks = {tuple(int(v) for v in l.kernel_size) for l in layers}
         if len(ks) != 1:
             raise ValueError(f"all GENEO kernels of an observer must share one kernel_size, got {ks}")

@@ -86,10 +86,10 @@ class PeerAllReduce:
         """in-place sum over ranks of a contiguous float32 CUDA vector (<= 96 elements)"""
         if flat.dtype != torch.float32 or not flat.is_cuda or not flat.is_contiguous():
             raise TypeError("peer all-reduce: contiguous float32 CUDA vector expected")
-        with torch.cuda.device(flat.device):
+        from .ops import _on_device, _stream
+        with _on_device(flat.device):
             self._check(self._lib.sn_peer_allreduce(flat.data_ptr(), flat.numel(), self.rank, self.world, self.ptrs,
-                                                    self.seq.data_ptr(), self.status.data_ptr(),
-                                                    torch.cuda.current_stream().cuda_stream), "sn_peer_allreduce")
+                                                    self.seq.data_ptr(), self.status.data_ptr(), _stream()), "sn_peer_allreduce")
         return flat
 
     def ok(self) -> bool:

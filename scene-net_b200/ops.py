@@ -19,7 +19,46 @@ _DT = {torch.float32: SN_F32, torch.float64: SN_F64}
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """raw cudaStream_t of torch's current stream on the current device (torch.cuda.current_stream() costs ~10 us of
+    host time per call; seven calls per step were a fifth of the eager step)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+_STREAM_OBJS: dict = {}
+
+
+def current_stream_obj(device) -> torch.cuda.Stream:
+    """torch.cuda.current_stream(device) through a cache keyed by the raw handle (the stock call is ~10 us)"""
+    idx = device.index if device.index is not None else torch._C._cuda_getDevice()
+    raw = torch._C._cuda_getCurrentRawStream(idx)
+    key = (idx, raw)
+    st = _STREAM_OBJS.get(key)
+    if st is None:
+        st = torch.cuda.current_stream(device)
+        if st.cuda_stream != raw:  # cannot happen; be safe
+            return st
+        _STREAM_OBJS[key] = st
+    return st
+
+
+class _on_device:
+    """`with _on_device(d)` without the cost when `d` is already the current device (the common case)"""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch._C._cuda_getDevice()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch._C._cuda_getDevice()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _need_cuda(t: torch.Tensor, name: str):
@@ -50,6 +89,13 @@ class ObserverSpec:
         return n + (len(self.kinds) if self.observer else 0)
 
     def desc(self) -> ModelDesc:
+        d = self.__dict__.get("_desc_cache")
+        if d is None:
+            d = self._build_desc()
+            self.__dict__["_desc_cache"] = d
+        return d
+
+    def _build_desc(self) -> ModelDesc:
         G = len(self.kinds)
         if G < 1 or G > _lib.SN_MAX_GENEOS:
             raise ValueError(f"between 1 and {_lib.SN_MAX_GENEOS} GENEO operators are supported, got {G}")
@@ -116,11 +162,15 @@ def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lam
         raise ValueError(f"expected {d.n_param_ptrs} parameter tensors, got {len(params)}")
     dev = params[0].device
     G, T = len(spec.kinds), spec.taps
-    K = torch.empty((G, *spec.kernel_size), dtype=torch.float32, device=dev)
-    snap = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=dev)
-    lam = torch.empty(G, dtype=torch.float32, device=dev) if spec.observer else None
-    Kstar = torch.empty(tuple(spec.kernel_size), dtype=torch.float32, device=dev) if spec.observer else None
-    with torch.cuda.device(dev):
+    # one allocation for the four small outputs (views into it): K | Kstar | lambda_eff | snapshot, each 16-byte aligned
+    Tp = (T + 3) & ~3
+    n_k, n_ks, n_l, n_s = G * Tp, (Tp if spec.observer else 0), (((G + 3) & ~3) if spec.observer else 0), d.n_param_ptrs
+    buf = torch.empty(n_k + n_ks + n_l + n_s, dtype=torch.float32, device=dev)
+    K = buf[:G * T].view(G, *spec.kernel_size)
+    Kstar = buf[n_k:n_k + T].view(tuple(spec.kernel_size)) if spec.observer else None
+    lam = buf[n_k + n_ks:n_k + n_ks + G] if spec.observer else None
+    snap = buf[n_k + n_ks + n_l:]
+    with _on_device(dev):
         check(lib.sn_geneo_synth_fwd(C.byref(d), _ptr_array(params), K.data_ptr(), _ptr(lam), _ptr(Kstar),
                                      snap.data_ptr(), int(write_last_lambda), _stream()), "sn_geneo_synth_fwd")
     return K, lam, Kstar, snap
@@ -132,7 +182,7 @@ def synth_bwd(spec: ObserverSpec, snapshot: torch.Tensor, dK: torch.Tensor) -> t
     _need_cuda(dK, "dK")
     dK = dK.to(torch.float64).contiguous()
     out = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=dK.device)
-    with torch.cuda.device(dK.device):
+    with _on_device(dK.device):
         check(lib.sn_geneo_synth_bwd(C.byref(d), _snapshot_ptr_array(snapshot), dK.data_ptr(), out.data_ptr(), _stream()),
               "sn_geneo_synth_bwd")
     return out
@@ -142,7 +192,7 @@ def param_grads(spec: ObserverSpec, snapshot: torch.Tensor, K: torch.Tensor, lam
                 scale: float = 1.0) -> torch.Tensor:
     d = spec.desc()
     out = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=W.device)
-    with torch.cuda.device(W.device):
+    with _on_device(W.device):
         check(lib.sn_scenenet_param_grads(C.byref(d), _snapshot_ptr_array(snapshot), K.data_ptr(), lambda_eff.data_ptr(),
                                           W.data_ptr(), float(scale), out.data_ptr(), _stream()), "sn_scenenet_param_grads")
     return out
@@ -160,7 +210,7 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
             x = x.clone()
         out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
         if x.numel():
-            with torch.cuda.device(x.device):
+            with _on_device(x.device):
                 check(lib.sn_cast_u8_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "sn_cast_u8_to_f32")
         return out
     if x.dtype != torch.float64:
@@ -169,7 +219,7 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     if x.numel() == 0:
         return out
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(lib.sn_cast_f64_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "sn_cast_f64_to_f32")
     return out
 
@@ -193,9 +243,9 @@ def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
         return x32, torch.zeros(2, dtype=torch.int64, device=x.device)
     nnz = torch.empty(2, dtype=torch.int64, device=x.device)  # [0] non-zero count, [1] ticket counter of the backward
     dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         if stream is not None:
-            stream.wait_stream(torch.cuda.current_stream(x.device))  # x (and any copy made above) is ready
+            stream.wait_stream(current_stream_obj(x.device))  # x (and any copy made above) is ready
         st = _stream() if stream is None else stream.cuda_stream
         check(lib.sn_grid_prepare(x.data_ptr(), dt, x.numel(), None if x.dtype == torch.float32 else x32.data_ptr(),
                                   nnz.data_ptr(), st), "sn_grid_prepare")
@@ -219,7 +269,7 @@ def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype,
     pred = torch.empty(x32.shape, dtype=out_dtype, device=x32.device)
     if x32.numel() == 0:
         return pred
-    with torch.cuda.device(x32.device):
+    with _on_device(x32.device):
         check(lib.sn_scenenet_fwd(x32.data_ptr(), _ptr(nnz), int(mode), Kstar.data_ptr(), B, Z, X, Y, kz, kx, ky, pred.data_ptr(),
                                   _DT[out_dtype], _stream()), "sn_scenenet_fwd")
     return pred
@@ -229,7 +279,8 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    idx = device.index if device.index is not None else torch._C._cuda_getDevice()
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx))
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -257,7 +308,7 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
         return W.zero_()
     nbytes = int(lib.sn_scenenet_bwd_workspace_bytes(B, Z, X, Y, kz, kx, ky))
     ws = _workspace(nbytes, x32.device)
-    with torch.cuda.device(x32.device):
+    with _on_device(x32.device):
         check(lib.sn_scenenet_bwd(x32.data_ptr(), _ptr(nnz), int(mode), pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype],
                                   B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
               "sn_scenenet_bwd")
@@ -276,7 +327,7 @@ def select_paths(x: torch.Tensor, kernel_size) -> tuple:
 def g0(pred: torch.Tensor, dpred: torch.Tensor) -> torch.Tensor:
     """G0 = dpred * (1 - pred^2) * [pred > 0] as float32 (pass 1 of the backward)."""
     out = torch.empty(pred.shape, dtype=torch.float32, device=pred.device)
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         check(lib.sn_scenenet_g0(pred.data_ptr(), _DT[pred.dtype], dpred.data_ptr(), _DT[dpred.dtype], pred.numel(),
                                  out.data_ptr(), _stream()), "sn_scenenet_g0")
     return out
@@ -289,7 +340,7 @@ def tapgrad(x32: torch.Tensor, g0_: torch.Tensor, kernel_size, nnz: Optional[tor
     kz, kx, ky = (int(v) for v in kernel_size)
     W = torch.empty((kz, kx, ky), dtype=torch.float64, device=x32.device)
     ws = _workspace(int(lib.sn_scenenet_tapgrad_workspace_bytes(B, Z, X, Y, kz, kx, ky)), x32.device)
-    with torch.cuda.device(x32.device):
+    with _on_device(x32.device):
         check(lib.sn_scenenet_tapgrad(x32.data_ptr(), g0_.data_ptr(), _ptr(nnz), int(mode), B, Z, X, Y, kz, kx, ky, W.data_ptr(), ws.data_ptr(),
                                       ws.numel(), _stream()), "sn_scenenet_tapgrad")
     return W
@@ -341,7 +392,7 @@ def criterion_fwd(pred: torch.Tensor, y: torch.Tensor, spec: CriterionSpec):
     coef = torch.empty(_lib.SN_CRIT_COEF, dtype=torch.float64, device=pred.device)
     ws = _workspace(int(lib.sn_criterion_workspace_bytes(n)), pred.device)
     r, w, nb = spec.arrays()
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         check(lib.sn_criterion_fwd(pred.data_ptr(), y.data_ptr(), _DT[pred.dtype], n, r, w, nb, float(spec.mse_weight),
                                    float(spec.tversky_alpha), float(spec.tversky_beta), float(spec.focal_gamma),
                                    float(spec.tversky_smooth), int(spec.terms), loss.data_ptr(), coef.data_ptr(), ws.data_ptr(),
@@ -356,7 +407,7 @@ def criterion_bwd(pred: torch.Tensor, y: torch.Tensor, coef: torch.Tensor, spec:
     if grad_out is not None:
         grad_out = grad_out.to(pred.dtype).reshape(1)
     r, w, nb = spec.arrays()
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         check(lib.sn_criterion_bwd(pred.data_ptr(), y.data_ptr(), _DT[pred.dtype], pred.numel(), r, w, nb, coef.data_ptr(),
                                    _ptr(grad_out), out.data_ptr(), int(as_g0), _stream()), "sn_criterion_bwd")
     return out
@@ -369,7 +420,7 @@ def param_penalty(params: Sequence[torch.Tensor], roles: Sequence[int], weight: 
         raise ValueError(f"at most {_lib.SN_MAX_PARAM_PTRS} parameters")
     dev = params[0].device
     out = torch.empty(2 + n, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         check(lib.sn_param_penalty(_ptr_array(params), (C.c_int32 * n)(*[int(r) for r in roles]), n, float(weight),
                                    out.data_ptr(), _stream()), "sn_param_penalty")
     return out
@@ -381,7 +432,7 @@ def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
         raise TypeError(f"threshold: float32/float64 only, got {p.dtype}")
     p = p.contiguous()
     out = torch.empty_like(p)
-    with torch.cuda.device(p.device):
+    with _on_device(p.device):
         check(lib.sn_threshold(p.data_ptr(), _DT[p.dtype], float(tau), p.numel(), out.data_ptr(), _stream()), "sn_threshold")
     return out
 
@@ -392,7 +443,7 @@ def fp32_peak_probe(iters: int = 2000, device=None) -> float:
     sink = torch.zeros(1, dtype=torch.float32, device=device)
     flops = C.c_double(0.0)
     best = 0.0
-    with torch.cuda.device(device):
+    with _on_device(device):
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

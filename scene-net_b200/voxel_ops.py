@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from ._lib import SN_F32, SN_F64, check, lib
-from .ops import _need_cuda, _ptr, _stream
+from .ops import _need_cuda, _on_device, _ptr, _stream
 
 _keep_cache: dict = {}
 
@@ -34,7 +34,7 @@ def bounding_boxes(points: torch.Tensor, offsets: Optional[torch.Tensor]) -> tor
     _need_cuda(points, "points")
     C_ = 1 if offsets is None else offsets.numel() - 1
     out = torch.empty((C_, 6), dtype=torch.float64, device=points.device)
-    with torch.cuda.device(points.device):
+    with _on_device(points.device):
         check(lib.sn_vox_minmax(points.data_ptr(), points.stride(0), _ptr(offsets), C_, points.shape[0], out.data_ptr(), _stream()),
               "sn_vox_minmax")
     return out
@@ -44,7 +44,7 @@ def grid_edges(mnmx: torch.Tensor, grid_xyz: Sequence[int]) -> torch.Tensor:
     nx, ny, nz = (int(v) for v in grid_xyz)
     C_ = mnmx.shape[0]
     out = torch.empty((C_, nx + ny + nz + 3), dtype=torch.float64, device=mnmx.device)
-    with torch.cuda.device(mnmx.device):
+    with _on_device(mnmx.device):
         check(lib.sn_vox_edges(mnmx.data_ptr(), C_, nx, ny, nz, out.data_ptr(), _stream()), "sn_vox_edges")
     return out
 
@@ -74,7 +74,7 @@ def voxelize_clouds(points: torch.Tensor, offsets: Optional[torch.Tensor] = None
     if need_keep and (labels is None or keep_labels is None):
         raise ValueError("frac / occ_keep need labels and keep_labels")
     keep_t = _keep_tensor(keep_labels, dev) if need_keep else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if edges is None:
             mnmx = bounding_boxes(points, offsets)
             edges = grid_edges(mnmx, (nx, ny, nz))
