@@ -580,8 +580,25 @@ def main():
         b_.record()
         b_.synchronize()
         train_ms = a_.elapsed_time(b_) / args.steps
+        # the same step with the observer and the criterion as ONE autograd node (criterion.training_loss: G0 comes
+        # straight from the criterion's backward; an extension next to the drop-in path)
+        sgraphs = [GraphedStep(model, pool[s_][0], loss_from_input=(lambda x_, y=ys[s_]: crit.training_loss(model, x_, y)),
+                               specialize=True) for s_ in range(n_sets)]
+        for i in range(args.warmup):
+            sgraphs[i % n_sets].replay()
+        torch.cuda.synchronize()
+        a_.record()
+        for i in range(args.steps):
+            sgraphs[(args.warmup + i) % n_sets].replay()
+        b_.record()
+        b_.synchronize()
+        single_ms = a_.elapsed_time(b_) / args.steps
+        single_loss = float(sgraphs[0].loss.detach())
+        del sgraphs
         train_value = {"value": B_PER_GPU / (train_ms * 1e-3), "unit": UNIT, "ms_per_step": train_ms,
-                       "loss": float(tgraphs[0].loss),
+                       "loss": float(tgraphs[0].loss.detach()),
+                       "single_node": {"value": B_PER_GPU / (single_ms * 1e-3), "unit": UNIT, "ms_per_step": single_ms, "loss": single_loss,
+                                       "note": "criterion.training_loss(model, x, y): no dL/dpred tensor, no separate G0 pass"},
                        "note": "config 2(ii): forward + GENEO_Tversky_Loss (drop-in class, fused reduction / closed-form "
                                "dL/dpred kernels, penalties on the live parameters) + backward, CUDA-graph replay"}
         del tgraphs

@@ -119,6 +119,14 @@ class GENEO_Tversky_Loss(GENEO_Loss):
         cvx_penalty, non_positive_penalty = self._both_penalties(cvx_coeffs, geneo_params)
         return dense_and_tversky + cvx_penalty + non_positive_penalty
 
+    def training_loss(self, model, x: torch.Tensor, y_gt: torch.Tensor):
+        """(loss, pred) of `model` on (x, y_gt) — extension: the observer forward and this criterion as ONE autograd
+        node (SceneNet.forward_with_criterion): the backward emits G0 directly, dL/dpred is never materialised.
+        Same value and gradients as `self(model(x), y_gt, model.get_cvx_coefficients(), model.get_geneo_params())`."""
+        dense_and_tversky, pred = model.forward_with_criterion(x, y_gt, self.fused_spec())
+        cvx_penalty, non_positive_penalty = self._both_penalties(model.get_cvx_coefficients(), model.get_geneo_params())
+        return dense_and_tversky + cvx_penalty + non_positive_penalty, pred
+
     @staticmethod
     def add_model_specific_args(parent_parser):
         parent_parser = GENEO_Loss.add_model_specific_args(parent_parser)

@@ -35,6 +35,56 @@ def _side_stream(device) -> torch.cuda.Stream:
     return st
 
 
+def _finish_backward(ctx, W):
+    """tap gradient -> parameter gradients (+ the gradient all-reduce), shared by the two autograd functions"""
+    x32, pred, K, lam, snap, nnz = ctx.saved_tensors[:6]
+    d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
+    if ctx.sync_group is not None:
+        # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
+        # no pack / unpack kernels; the parameter .grads are views into it
+        if callable(ctx.sync_group):
+            ctx.sync_group(d)  # dist.PeerAllReduce: our single-kernel exchange over NVLink peer memory
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
+    return d
+
+
+class _ObserverLossFunction(torch.autograd.Function):
+    """(loss, pred) with loss = weighted MSE + focal Tversky of pred against y (csrc/criterion.cu) — the observer and
+    the criterion as ONE autograd node: the backward turns the criterion's closed-form dL/dpred straight into
+    G0 = dL/dpred (1 - pred^2) [pred > 0] (sn_criterion_bwd with out_g0), so neither dL/dpred (67 MB at config 2) nor
+    the separate G0 pass (168 MB of traffic) exists.  An extension next to the drop-in path (model(x) followed by the
+    criterion), with bit-identical loss and gradients."""
+
+    @staticmethod
+    def forward(ctx, x, y, spec, crit_spec, write_last, grad_scale, sync_group, path_modes, *params):
+        cur = ops.current_stream_obj(x.device)
+        side = _side_stream(x.device)
+        x32, nnz = ops.prepare(x.detach(), stream=side)
+        K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
+        cur.wait_stream(side)
+        pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz,
+                                mode=path_modes[0])
+        loss, coef, p, t = ops.criterion_fwd(pred, y.detach(), crit_spec)
+        ctx.bwd_mode = path_modes[1]
+        ctx.spec, ctx.crit_spec = spec, crit_spec
+        ctx.grad_scale, ctx.sync_group = grad_scale, sync_group
+        ctx.save_for_backward(x32, p, K, lam, snap, nnz, t, coef)
+        ctx.mark_non_differentiable(pred)
+        return (loss if pred.dtype == torch.float64 else loss.to(pred.dtype)), pred
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_pred):
+        x32, p, K, lam, snap, nnz, t, coef = ctx.saved_tensors
+        g0 = ops.criterion_bwd(p, t, coef, ctx.crit_spec, grad_out=g_loss, as_g0=True)
+        W = ops.tapgrad(x32, g0, ctx.spec.kernel_size, nnz=nnz, mode=ctx.bwd_mode)
+        d = _finish_backward(ctx, W)
+        unused = ctx.spec.unused
+        grads = [d[i] if (ctx.needs_input_grad[i + 8] and i not in unused) else None for i in range(d.numel())]
+        return (None,) * 8 + tuple(grads)
+
+
 class _ObserverFunction(torch.autograd.Function):
     """pred = relu(tanh(conv3d_same(x, sum_g lambda_g K_g(theta_g)))) with a hand-written backward."""
 
@@ -65,15 +115,7 @@ class _ObserverFunction(torch.autograd.Function):
     def backward(ctx, dpred):
         x32, pred, K, lam, snap, nnz = ctx.saved_tensors
         W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size, nnz, mode=ctx.bwd_mode)
-        d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
-        if ctx.sync_group is not None:
-            # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
-            # no pack / unpack kernels; the parameter .grads are views into it
-            if callable(ctx.sync_group):
-                ctx.sync_group(d)  # dist.PeerAllReduce: our single-kernel exchange over NVLink peer memory
-            else:
-                import torch.distributed as dist
-                dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
+        d = _finish_backward(ctx, W)
         unused = ctx.spec.unused
         grads = [d[i] if (ctx.needs_input_grad[i + 7] and i not in unused) else None for i in range(d.numel())]
         return (None, None, None, None, None, None, None, *grads)
@@ -267,6 +309,20 @@ class _SceneNetBase(nn.Module):
         # write_last=True reproduces the side effect of SCENE_Net.py:333 (last lambda <- 1 - sum(others)), in place
         return _ObserverFunction.apply(x, spec, True, float(self.grad_scale), self.grad_sync_group, tuple(self.path_modes),
                                        _prepared, *params)
+
+    def forward_with_criterion(self, x: torch.Tensor, y: torch.Tensor, crit_spec: "ops.CriterionSpec"):
+        """(loss, pred): forward + the fused criterion (weighted MSE + focal Tversky) as one autograd node — see
+        _ObserverLossFunction.  Extension; use through `GENEO_Tversky_Loss.training_loss(model, x, y)`."""
+        spec, params = self._spec_and_params()
+        if not params[0].is_cuda:
+            raise RuntimeError("scenenet_b200: the model lives on the CPU; move it with .cuda() — the hot path is "
+                               "CUDA-only (no CPU fallback)")
+        if x.device != params[0].device or y.device != x.device:
+            raise RuntimeError(f"input on {x.device} / target on {y.device} but model on {params[0].device}")
+        if y.shape != x.shape:
+            raise ValueError(f"target shape {tuple(y.shape)} differs from the grid shape {tuple(x.shape)}")
+        return _ObserverLossFunction.apply(x, y, spec, crit_spec, True, float(self.grad_scale), self.grad_sync_group,
+                                           tuple(self.path_modes), *params)
 
 
 class SCENE_Net(_SceneNetBase):

@@ -24,6 +24,7 @@ class GraphedStep:
 
     x:        static device input [B,1,Z,X,Y] (float32/float64); refill it (or `x_host`) between replays
     dpred:    static upstream gradient (same shape), or None when `loss_fn(pred) -> scalar` is given
+    loss_from_input: alternative to both: `x -> (loss, pred)` (e.g. `lambda x: criterion.training_loss(model, x, y)`)
     x_host:   optional pinned host tensor; when given every replay starts with x.copy_(x_host) (H2D)
     grads_host: optional pinned host float32 tensor [n_trainable]; when given every replay ends with the
               D2H copy of the flat gradient vector into it
@@ -36,9 +37,11 @@ class GraphedStep:
     def __init__(self, model: torch.nn.Module, x: torch.Tensor, dpred: Optional[torch.Tensor] = None,
                  loss_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, x_host: Optional[torch.Tensor] = None,
                  grads_host: Optional[torch.Tensor] = None, post_backward: Optional[Callable[[], None]] = None,
-                 warmup: int = 3, specialize: bool = False):
-        if (dpred is None) == (loss_fn is None):
-            raise ValueError("give exactly one of dpred / loss_fn")
+                 warmup: int = 3, specialize: bool = False,
+                 loss_from_input: Optional[Callable[[torch.Tensor], tuple]] = None):
+        if (dpred is not None) + (loss_fn is not None) + (loss_from_input is not None) != 1:
+            raise ValueError("give exactly one of dpred / loss_fn / loss_from_input")
+        self.loss_from_input = loss_from_input
         self.model, self.x, self.dpred, self.loss_fn = model, x, dpred, loss_fn
         self.x_host, self.grads_host, self.post_backward = x_host, grads_host, post_backward
         # specialize: read the occupancy of `x` once (host sync, before capture) and enqueue only the kernels the
@@ -68,17 +71,22 @@ class GraphedStep:
     def _step(self):
         if self.x_host is not None:
             self.x.copy_(self.x_host, non_blocking=True)
+        saved = None
         if self.path_modes is not None:
             saved, self.model.path_modes = self.model.path_modes, self.path_modes
-            try:
+        try:
+            if self.loss_from_input is not None:  # e.g. criterion.training_loss(model, x, y): one autograd node
+                self.loss, self.pred = self.loss_from_input(self.x)
+            else:
                 self.pred = self.model(self.x)
-            finally:
+        finally:
+            if saved is not None:
                 self.model.path_modes = saved
-        else:
-            self.pred = self.model(self.x)
         # torch.autograd.grad instead of .backward(): no AccumulateGrad nodes take part, so parameters that
         # were already used eagerly (their AccumulateGrad lives on the legacy stream) cannot break the capture
-        if self.loss_fn is not None:
+        if self.loss_from_input is not None:
+            grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
+        elif self.loss_fn is not None:
             self.loss = self.loss_fn(self.pred)
             grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
         else:

@@ -135,3 +135,39 @@ def test_weight_table_matches_reference_ops():
     dens = crit.get_dens_target(y)
     w = torch.max(1 - dens, torch.full_like(dens, 0.1))
     assert [float(v) for v in w] == w_raw
+
+
+def test_training_loss_single_node_equals_two_step_path():
+    """criterion.training_loss(model, x, y) (observer + criterion as one autograd node, G0 emitted by the criterion's
+    backward) gives the bits of criterion(model(x), y, ...)"""
+    sb = _sb()
+    x, y = mo.synthetic_grids(2, (32, 32, 32), seed=31)
+    x, y = x.to(DEV), y.to(DEV)
+
+    def make():
+        torch.manual_seed(0)
+        m = sb.SceneNet({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5)).to(DEV)
+        with torch.no_grad():
+            for name, layer in m.geneos.items():
+                for pn, p in layer.geneo_params.items():
+                    p.fill_(float(mo.KAT_PARAMS[f"{name}.{pn}"]))
+            for ln, p in m.lambdas_dict.items():
+                p.fill_(float(mo.KAT_LAMBDAS[ln]))
+                p.requires_grad_(ln != mo.KAT_LAST)
+        m.last_lambda = mo.KAT_LAST
+        return m
+
+    crit = sb.GENEO_Tversky_Loss(hist=HIST, **KW)
+    m1 = make()
+    pred1 = m1(x)
+    l1 = crit(pred1, y, m1.get_cvx_coefficients(), m1.get_geneo_params())
+    l1.backward()
+    m2 = make()
+    l2, pred2 = crit.training_loss(m2, x, y)
+    l2.backward()
+    assert torch.equal(pred1.detach(), pred2) and not pred2.requires_grad
+    assert float(l1) == float(l2)
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert (p1.grad is None) == (p2.grad is None), n1
+        if p1.grad is not None:
+            assert torch.equal(p1.grad, p2.grad), (n1, float(p1.grad), float(p2.grad))
