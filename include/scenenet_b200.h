@@ -265,6 +265,14 @@ int sn_vox_bin(const double* pts, int ld, const double* labels, int label_ld, co
                const double* keep, int n_keep, int32_t* count, int32_t* keep_count, double* max_label,
                int32_t* lin_out, void* stream);
 
+/* Steps 1-3 in three launches instead of five (one initialisation kernel; the binning kernel derives the edges from
+ * the bounding boxes itself and publishes them): same outputs as sn_vox_minmax + sn_vox_edges + sn_vox_bin, bit for
+ * bit.  mnmx [C,6], edges [C, nx+ny+nz+3] float64 out; the other arguments as in sn_vox_bin. */
+int sn_vox_voxelize(const double* pts, int ld, const double* labels, int label_ld, const int64_t* offsets,
+                    int n_clouds, int64_t n_points_total, int nx, int ny, int nz, const double* keep, int n_keep,
+                    double* mnmx, double* edges, int32_t* count, int32_t* keep_count, double* max_label,
+                    int32_t* lin_out, void* stream);
+
 /* Step 4: finalize.  density = MinMax-normalised count per y column (float64, sklearn
  * semantics), frac = keep/count (0 where empty), max_label keys -> float64 in place (0 where
  * empty), occ = (count>0), occ_keep = (keep_count>0) as 0/1 in out_dtype.  Any output may be

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_vox_edges": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sn_vox_bin": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sn_vox_voxelize": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sn_vox_finalize_workspace_bytes": (_i64, [_i, _i]),
     "sn_vox_finalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sn_peer_allreduce_buffer_bytes": (_i64, [_i]),

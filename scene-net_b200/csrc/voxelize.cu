@@ -107,9 +107,8 @@ minmax_kernel(const double* __restrict__ pts, int ld, const long long* __restric
 
 // ------------------------------------------------------------------ step 2: edges
 // pyntcloud VoxelGrid.compute (regular_bounding_box=True) + np.linspace, op by op.
-__global__ void edges_kernel(const double* __restrict__ mnmx, int nx, int ny, int nz, double* __restrict__ edges) {
-    const int c = blockIdx.x;
-    const double* b = mnmx + c * 6;
+// all threads of the CTA: the nx+1, ny+1, nz+1 edges of one cloud from its bounding box b[6] into e[]
+__device__ __forceinline__ void compute_edges(const double* __restrict__ b, int nx, int ny, int nz, double* __restrict__ e) {
     double rng[3], lo[3], hi[3];
     for (int k = 0; k < 3; ++k) rng[k] = __dsub_rn(b[3 + k], b[k]);  // ptp
     const double rmax = fmax(rng[0], fmax(rng[1], rng[2]));
@@ -121,7 +120,6 @@ __global__ void edges_kernel(const double* __restrict__ mnmx, int nx, int ny, in
     }
     const int n[3] = {nx, ny, nz};
     const int base[3] = {0, nx + 1, nx + 1 + ny + 1};
-    double* e = edges + (size_t)c * (nx + ny + nz + 3);
     for (int k = 0; k < 3; ++k) {
         const double delta = __dsub_rn(hi[k], lo[k]);
         const double step = __ddiv_rn(delta, (double)n[k]);
@@ -135,6 +133,23 @@ __global__ void edges_kernel(const double* __restrict__ mnmx, int nx, int ny, in
                 v = __dadd_rn(__dmul_rn((double)j, step), lo[k]);
             e[base[k] + j] = v;
         }
+    }
+}
+
+__global__ void edges_kernel(const double* __restrict__ mnmx, int nx, int ny, int nz, double* __restrict__ edges) {
+    const int c = blockIdx.x;
+    compute_edges(mnmx + c * 6, nx, ny, nz, edges + (size_t)c * (nx + ny + nz + 3));
+}
+
+// one launch for every initialisation of the fused entry point: bounding boxes to +-inf, grids to 0 / lowest key
+__global__ void vox_init_kernel(double* __restrict__ mnmx, int n_clouds, int* __restrict__ count, int* __restrict__ keep_count,
+                                long long* __restrict__ maxkey, long long n) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = i0; i < (long long)n_clouds * 6; i += stride) mnmx[i] = (i % 6) < 3 ? INFINITY : -INFINITY;
+    for (long long i = i0; i < n; i += stride) {
+        count[i] = 0;
+        if (keep_count) keep_count[i] = 0;
+        if (maxkey) maxkey[i] = (long long)0x8000000000000000ULL;
     }
 }
 
@@ -170,11 +185,21 @@ __global__ void __launch_bounds__(kVoxThreads)
 bin_kernel(const double* __restrict__ pts, int ld, const double* __restrict__ labels, int label_ld,
            const long long* __restrict__ offsets, const double* __restrict__ edges, int nx, int ny, int nz,
            const double* __restrict__ keep, int n_keep, int* __restrict__ count, int* __restrict__ keep_count,
-           long long* __restrict__ maxkey, int* __restrict__ lin_out, long long n_total) {
+           long long* __restrict__ maxkey, int* __restrict__ lin_out, long long n_total, const double* __restrict__ mnmx,
+           double* __restrict__ edges_out) {
     extern __shared__ double s_edges[];  // (nx+1)+(ny+1)+(nz+1) doubles, n_keep keep labels, then the aggregation table
     const int c = blockIdx.y;
     const int ne = nx + ny + nz + 3;
-    for (int i = threadIdx.x; i < ne; i += blockDim.x) s_edges[i] = edges[(size_t)c * ne + i];
+    if (mnmx) {
+        // fused entry point: every CTA derives its cloud's edges from the bounding box itself (3 x 65 values: cheaper
+        // than a launch); the first CTA of the cloud also publishes them
+        compute_edges(mnmx + c * 6, nx, ny, nz, s_edges);
+        __syncthreads();
+        if (blockIdx.x == 0 && edges_out)
+            for (int i = threadIdx.x; i < ne; i += blockDim.x) edges_out[(size_t)c * ne + i] = s_edges[i];
+    } else {
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) s_edges[i] = edges[(size_t)c * ne + i];
+    }
     double* s_keep = s_edges + ne;
     for (int i = threadIdx.x; i < n_keep; i += blockDim.x) s_keep[i] = keep[i];
     int* s_key = reinterpret_cast<int*>(s_keep + n_keep + (n_keep & 1));  // table behind the doubles
@@ -386,7 +411,41 @@ extern "C" int sn_vox_bin(const double* pts, int ld, const double* labels, int l
     bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
     sn::bin_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, smem, s>>>(pts, ld, labels, label_ld, (const long long*)offsets, edges,
                                                                     nx, ny, nz, keep, n_keep, count, keep_count,
-                                                                    (long long*)max_label, lin_out, n_points_total);
+                                                                    (long long*)max_label, lin_out, n_points_total, nullptr, nullptr);
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int sn_vox_voxelize(const double* pts, int ld, const double* labels, int label_ld, const int64_t* offsets,
+                               int n_clouds, int64_t n_points_total, int nx, int ny, int nz, const double* keep, int n_keep,
+                               double* mnmx, double* edges, int32_t* count, int32_t* keep_count, double* max_label,
+                               int32_t* lin_out, void* stream) {
+    if (!pts || !mnmx || !edges || !count || ld < 3 || n_clouds < 1 || n_clouds > 65535) return SN_ERR_BAD_ARG;
+    if (!offsets && n_clouds != 1) return SN_ERR_BAD_ARG;
+    if (nx < 1 || ny < 1 || nz < 1 || n_keep < 0 || (n_keep > 0 && !keep) || n_points_total < 0) return SN_ERR_BAD_ARG;
+    if ((long long)nx * ny * nz > 0x7fffffffLL) return SN_ERR_UNSUPPORTED;
+    if (labels && label_ld < 1) return SN_ERR_BAD_ARG;
+    if ((size_t)(nx + ny + nz + 3 + n_keep) * sizeof(double) > 48 * 1024) return SN_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(nx + ny + nz + 3 + n_keep + (n_keep & 1)) * sizeof(double) + 3 * sn::kBinSlots * sizeof(int);
+    cudaError_t ea = cudaFuncSetAttribute(sn::bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return sn::cuda_rc(ea);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nvox = (long long)n_clouds * nx * ny * nz;
+    // 1. every initialisation in one launch
+    sn::vox_init_kernel<<<sn::blocks_for(nvox), sn::kVoxThreads, 0, s>>>(mnmx, n_clouds, count, keep_count, (long long*)max_label, nvox);
+    SN_LAUNCH_CHECK();
+    // 2. bounding boxes
+    const int bxm = max(1, sn::kNumSMs * 4 / n_clouds);
+    sn::minmax_kernel<<<dim3(bxm, n_clouds), sn::kVoxThreads, 0, s>>>(pts, ld, (const long long*)offsets, n_points_total, mnmx);
+    SN_LAUNCH_CHECK();
+    // 3. binning; the edges are derived from the boxes inside the kernel and published by the first CTA of each cloud
+    const long long per_cloud = sn::ceil_div64(n_points_total > 0 ? n_points_total : 1, n_clouds);
+    int bx = (int)sn::ceil_div64(per_cloud, sn::kVoxThreads * sn::kBinUnroll);
+    const int cap = max(1, sn::kNumSMs * 8 / n_clouds);
+    bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+    sn::bin_kernel<<<dim3(bx, n_clouds), sn::kVoxThreads, smem, s>>>(pts, ld, labels, label_ld, (const long long*)offsets, nullptr,
+                                                                    nx, ny, nz, keep, n_keep, count, keep_count,
+                                                                    (long long*)max_label, lin_out, n_points_total, mnmx, edges);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -75,18 +75,24 @@ def voxelize_clouds(points: torch.Tensor, offsets: Optional[torch.Tensor] = None
         raise ValueError("frac / occ_keep need labels and keep_labels")
     keep_t = _keep_tensor(keep_labels, dev) if need_keep else None
     with _on_device(dev):
-        if edges is None:
-            mnmx = bounding_boxes(points, offsets)
-            edges = grid_edges(mnmx, (nx, ny, nz))
         shape = (C_, nz, nx, ny)
         count = torch.empty(shape, dtype=torch.int32, device=dev)
         keep_count = torch.empty(shape, dtype=torch.int32, device=dev) if need_keep else None
         maxlab = torch.empty(shape, dtype=torch.float64, device=dev) if "max_label" in want else None
         lin = torch.empty(N, dtype=torch.int32, device=dev) if return_lin else None
-        check(lib.sn_vox_bin(points.data_ptr(), points.stride(0), _ptr(labels), labels.stride(0) if labels is not None else 0,
-                             _ptr(offsets), C_, N, edges.data_ptr(), nx, ny, nz, _ptr(keep_t),
-                             0 if keep_t is None else keep_t.numel(), count.data_ptr(), _ptr(keep_count), _ptr(maxlab),
-                             _ptr(lin), _stream()), "sn_vox_bin")
+        lab_ld = labels.stride(0) if labels is not None else 0
+        n_keep = 0 if keep_t is None else keep_t.numel()
+        if edges is None:
+            # bounding boxes -> edges -> binning in three launches (one init kernel, edges derived inside the binning kernel)
+            mnmx = torch.empty((C_, 6), dtype=torch.float64, device=dev)
+            edges = torch.empty((C_, nx + ny + nz + 3), dtype=torch.float64, device=dev)
+            check(lib.sn_vox_voxelize(points.data_ptr(), points.stride(0), _ptr(labels), lab_ld, _ptr(offsets), C_, N, nx, ny, nz,
+                                      _ptr(keep_t), n_keep, mnmx.data_ptr(), edges.data_ptr(), count.data_ptr(), _ptr(keep_count),
+                                      _ptr(maxlab), _ptr(lin), _stream()), "sn_vox_voxelize")
+        else:
+            check(lib.sn_vox_bin(points.data_ptr(), points.stride(0), _ptr(labels), lab_ld, _ptr(offsets), C_, N, edges.data_ptr(),
+                                 nx, ny, nz, _ptr(keep_t), n_keep, count.data_ptr(), _ptr(keep_count), _ptr(maxlab), _ptr(lin),
+                                 _stream()), "sn_vox_bin")
         density = torch.empty(shape, dtype=torch.float64, device=dev) if "density" in want else None
         frac = torch.empty(shape, dtype=torch.float64, device=dev) if "frac" in want else None
         occ = torch.empty(shape, dtype=occ_dtype, device=dev) if "occ" in want else None
