@@ -120,34 +120,33 @@ __device__ __forceinline__ void last_cta_row_sum(unsigned long long* ticket, con
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // warp g sums rows g, g + G, ... (lanes <-> taps, 8 loads in flight per lane), then the G group sums are added in
-    // group order: a fixed order whatever the timing (a single pass of T threads over all rows took ~7 us)
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-    const int G = nwarps < kRowSumGroups ? nwarps : kRowSumGroups;
+    // row group g (TW threads each) sums rows g, g + G, ...; a thread owns one tap per sweep and keeps 16 loads in flight;
+    // the G group sums are then added in group order: a fixed order whatever the timing
+    const int TW = nthreads >= 256 ? 256 : nthreads;
+    const int G = nthreads / TW < kRowSumGroups ? nthreads / TW : kRowSumGroups;
+    const int g = tid / TW, tl = tid % TW;
     for (int t0 = 0; t0 < T; t0 += 256) {  // 256 taps per sweep (scratch [G][256])
-        if (warp < G) {
-            for (int tt = lane; tt < 256; tt += 32) {
-                const int t = t0 + tt;
+        if (g < G) {
+            for (int tq = tl; tq < 256; tq += TW) {
+                const int tc = t0 + tq;
                 double a = 0.0;
-                if (t < T) {
-                    int r = warp;
-                    for (; r + 7 * G < rows; r += 8 * G) {
-                        double v[8];
+                if (tc < T) {
+                    for (int r = g; r < rows; r += 16 * G) {
+                        double v[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __ldcg(partial + (size_t)(r + i * G) * TP + t);
+                        for (int i = 0; i < 16; ++i) v[i] = (r + i * G < rows) ? __ldcg(partial + (size_t)(r + i * G) * TP + tc) : 0.0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a += v[i];
+                        for (int i = 0; i < 16; ++i) a += v[i];
                     }
-                    for (; r < rows; r += G) a += __ldcg(partial + (size_t)r * TP + t);
                 }
-                scratch[warp * 256 + tt] = a;
+                scratch[g * 256 + tq] = a;
             }
         }
         __syncthreads();
-        for (int tt = tid; tt < 256 && t0 + tt < T; tt += nthreads) {
+        for (int tq = tid; tq < 256 && t0 + tq < T; tq += nthreads) {
             double a = 0.0;
-            for (int g = 0; g < G; ++g) a += scratch[g * 256 + tt];
-            W[t0 + tt] = a;
+            for (int q = 0; q < G; ++q) a += scratch[q * 256 + tq];
+            W[t0 + tq] = a;
         }
         __syncthreads();
     }
