@@ -87,17 +87,17 @@ class WeightedMSE(torch.nn.Module):
         self._table = None
 
     def hist_frequency_estimation(self, y: torch.Tensor, hist_len=10, plot=False):
-        """w_mse.py:71-112 (setup-time, not on the hot path): counts of y per decimal bin."""
-        hist_range = torch.linspace(0, 1, hist_len + 1, device=self.device)[:-1]
+        """(counts, bin starts) of y over `hist_len` equal bins of [0, 1) — setup time, not on the hot path
+        (w_mse.py:71-112)."""
         y = y.to(self.device)
-        hist_idxs = (hist_len * y).to(torch.int)
-        hist_count = torch.bincount(hist_idxs, minlength=hist_len)
+        starts = torch.linspace(0, 1, hist_len + 1, device=self.device)[:hist_len]
+        counts = torch.bincount((hist_len * y).to(torch.int), minlength=hist_len)
         if plot:
+            width = float(starts[1] - starts[0]) if hist_len > 1 else 1.0
             print("Histogram Bin /\t Count")
-            step = hist_range[1] - hist_range[0]
-            for i in range(len(hist_range)):
-                print(f"[{hist_range[i]:.3f}, {hist_range[i] + step:.3f}[ : {hist_count[i]}")
-        return hist_count, hist_range
+            for lo, c in zip(starts.tolist(), counts.tolist()):
+                print(f"[{lo:.3f}, {lo + width:.3f}[ : {c}")
+        return counts, starts
 
     # ------------------------------------------------------------------ the 10-entry weighting table
     def _weight_table(self):
@@ -114,6 +114,7 @@ class WeightedMSE(torch.nn.Module):
             dens = (hist_idx - freq_min) / (freq_max - freq_min)  # int64 / int64 -> float32
             w = torch.max(1 - self.weight_alpha * dens, torch.full_like(dens, self.weight_epsilon))
             self._table = ([float(v) for v in ranges.to(torch.float32)], [float(v) for v in w.to(torch.float32)])
+            self._dens_table, self._w_table = dens, w.to(torch.float32)
             self._table_key = key
         return self._table
 
@@ -121,23 +122,25 @@ class WeightedMSE(torch.nn.Module):
         ranges, w_raw = self._weight_table()
         return ops.CriterionSpec(ranges=ranges, w_raw=w_raw, mse_weight=float(self.mse_weight), terms=terms, **tversky)
 
+    def _bins(self, y: torch.Tensor) -> torch.Tensor:
+        """nearest histogram bin of every target value (first minimum, like torch.argmin in w_mse.py:120)"""
+        return (y.unsqueeze(-1) - self.ranges.to(y.device)).abs().argmin(dim=-1)
+
     def get_dens_target(self, y: torch.Tensor, calc_weights=False):
-        """w_mse.py:114-133, per voxel (diagnostic API; the fused forward does not call it)."""
+        """per-voxel density of the target's histogram bin (w_mse.py:114-133; diagnostic API, the fused forward never
+        materialises it): a lookup of the bin in the 10-entry table the reference's own ops produce"""
         if calc_weights:
             self.freqs, self.ranges = self.hist_frequency_estimation(y)
-        hist_idx = torch.abs(torch.unsqueeze(y, -1) - self.ranges).argmin(dim=-1)
-        for idx in range(len(self.freqs)):
-            hist_idx[hist_idx == idx] = self.freqs[idx]
-        freq_min, freq_max = torch.min(self.freqs), torch.max(self.freqs)
-        return (hist_idx - freq_min) / (freq_max - freq_min)
+            self._table_key = None
+        self._weight_table()
+        return self._dens_table.to(y.device)[self._bins(y)]
 
     def get_weight_target(self, y: torch.Tensor):
-        """w_mse.py:135-145 (diagnostic API)."""
+        """per-voxel weight max(1 - alpha * density, epsilon) / mean (w_mse.py:135-145; diagnostic API)"""
         y = y.to(self.device)
-        y_dens = self.get_dens_target(y)
-        weights = torch.max(1 - self.weight_alpha * y_dens, torch.full_like(y_dens, self.weight_epsilon, device=self.device))
-        assert weights.shape == y.shape
-        return weights / torch.mean(weights)
+        self._weight_table()
+        w = self._w_table.to(y.device)[self._bins(y)]
+        return w / w.mean()
 
     def forward(self, y_pred: torch.Tensor, y_gt: torch.Tensor):
         return _FusedCriterion.apply(y_pred, y_gt, self._spec(1))
