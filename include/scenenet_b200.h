@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 2
+#define SN_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define SN_OK 0
@@ -41,7 +41,9 @@ extern "C" {
 /* ---- dtypes of grid tensors crossing the boundary ------------------------------------ */
 #define SN_F32 0
 #define SN_F64 1
-#define SN_U8 2 /* occupancy bytes (uint8 / bool); accepted by sn_grid_prepare only */
+#define SN_U8 2  /* occupancy bytes (uint8 / bool); accepted by sn_grid_prepare and as a target dtype */
+#define SN_I32 3 /* integer targets (sn_confusion_counts only) */
+#define SN_I64 4
 
 /* ---- GENEO operator kinds (core/models/geneos/) -------------------------------------- */
 #define SN_KIND_CYLINDER_V1 0 /* cylinder.py:30-140   cylinder_kernel   params: radius, sigma                */
@@ -124,10 +126,10 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
  * Observer forward — replaces F.conv3d + convex combination + relu(tanh) of
  * SceneNet.forward / SCENE_Net.forward (SCENE_Net.py:209-226, 322-339).
  *   x     [B,1,Z,X,Y] float32          (sn_grid_prepare converts the reference's float64 grids)
- *   nnz   DEVICE pointer to the number of non-zero voxels of x (from sn_grid_prepare), or NULL
+ *   nnz   DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count + occupancy bits), or NULL
  *   mode  SN_PATH_AUTO: with nnz, the dense stencil and an occupancy-driven kernel (cost proportional to the
  *         occupied voxels) are both enqueued and the count selects ON THE DEVICE which of them works (sparse up
- *         to 1.25 % occupancy for kx*ky <= 32 taps per slice, 4 % above); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
+ *         to 3 % occupancy for kx*ky <= 64 taps per slice, 4 % above); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
  *         (measurement, tests).  Same pred either way up to float32 summation order.
  *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
  *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
@@ -220,10 +222,14 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
  * ====================================================================================== */
 /* Grid preparation, one HBM pass: x (SN_F64 as handed over by the reference's ToTensor, torch_transforms.py:13;
  * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
- * nothing is copied) and nnz[0] = number of non-zero voxels.  nnz: DEVICE buffer of TWO uint64, 16-byte aligned,
- * zeroed by the call: [0] the count, [1] a ticket counter the tap-gradient kernels use to let their last CTA
- * sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward).
+ * nothing is copied) and the grid STATE buffer `nnz` the forward / backward take:
+ *   [0] uint64 number of non-zero voxels, [1] uint64 ticket counter the tap-gradient kernels use to let their last
+ *   CTA sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward), then from
+ *   byte 16 one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel index i; ABI v3): the
+ *   occupancy-driven forward lists the non-zero voxels of a halo row from these words instead of scanning floats.
+ * nnz: DEVICE buffer of sn_grid_state_bytes(n) bytes, 16-byte aligned; counters zeroed and bits written by the call.
  * x and x32 16-byte aligned. */
+int64_t sn_grid_state_bytes(int64_t n);
 int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream);
 /* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */
 int sn_cast_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
@@ -232,6 +238,20 @@ int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n, void* stre
 /* prob_to_label (utils/voxelization.py:304-323) / SCENE_Net_Class.forward (SCENE_Net.py:465-466):
  * out = (p >= tau) as 0/1, same dtype as p. */
 int sn_threshold(const void* p, int dtype, double tau, int64_t n, void* out, void* stream);
+
+/* ======================================================================================
+ * Metric state — replaces the update of the torchmetrics 0.9.0 collection the reference
+ * builds in utils/scripts_utils.py:80-91 (JaccardIndex(num_classes=2) / Precision / Recall / F1Score /
+ * FBetaScore(beta=0.5), all with threshold tau) and feeds every step in core/lit_modules/lit_model_wrappers.py:
+ * 170-171 (train), 189-190 (validation), 199-200 (test): every one of them thresholds `preds >= tau` and counts
+ * against the integer target.  One pass over (pred, y):
+ *   counts = {TP, FP, TN, FN},  positive prediction <=> pred >= tau,  positive target <=> y != 0.
+ * pred: SN_F32 / SN_F64, 16-byte aligned (float32 predictions are compared with (float)tau like torch does);
+ * y: SN_F32 / SN_F64 / SN_U8 / SN_I32 / SN_I64, aligned to min(16, 16 / sizeof(pred) * sizeof(y)) bytes.
+ * batch_counts (nullable): DEVICE uint64[4], OVERWRITTEN with this call's counts; total_counts (nullable): DEVICE
+ * uint64[4], this call's counts are ADDED (the running state of an epoch).  At least one must be given. */
+int sn_confusion_counts(const void* pred, int pred_dtype, const void* y, int y_dtype, int64_t n, double tau,
+                        unsigned long long* batch_counts, unsigned long long* total_counts, void* stream);
 
 /* ======================================================================================
  * Voxelization — replaces eda.voxelize_ply (utils/pcd_processing.py:341-372 -> pyntcloud

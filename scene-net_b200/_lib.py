@@ -12,7 +12,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCENENET_B200_LIB", os.path.join(PKG, "libscenenet_b200.so"))  # override: experiments only
 
-SN_F32, SN_F64, SN_U8 = 0, 1, 2
+SN_F32, SN_F64, SN_U8, SN_I32, SN_I64 = 0, 1, 2, 3, 4
 SN_PATH_AUTO, SN_PATH_DENSE, SN_PATH_SPARSE = 0, 1, 2
 SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE = 0, 1, 2
 SN_MAX_GENEOS = 16
@@ -20,7 +20,7 @@ SN_MAX_PARAM_PTRS = 96
 SN_MAX_TAPS = 4096
 SN_CRIT_MAX_BINS = 12
 SN_CRIT_COEF = SN_CRIT_MAX_BINS + 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 KIND = {
     "cylinder_kernel": 0, "cylinderv2": 1, "cone_kernel": 2, "arrow": 3, "neg_sphere_kernel": 4, "negSpherev2": 5,
@@ -61,6 +61,7 @@ SIGNATURES = {
     "sn_scenenet_g0": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_scenenet_tapgrad_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_tapgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sn_grid_state_bytes": (_i64, [_i64]),
     "sn_grid_prepare": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "sn_criterion_workspace_bytes": (_i64, [_i64]),
     "sn_criterion_fwd": (_i, [_vp, _vp, _i, _i64, _fp, _fp, _i, C.c_float, _d, _d, _d, _d, _i, _vp, _vp, _vp, _i64, _vp]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),
+    "sn_confusion_counts": (_i, [_vp, _i, _vp, _i, _i64, _d, _vp, _vp, _vp]),
     "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_vox_edges": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sn_vox_bin": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

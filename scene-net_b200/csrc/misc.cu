@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(256) cast_u8_f32_kernel(const unsigned char* _
 
 
 // ---- sn_grid_prepare: cast to float32 + count the non-zero voxels (the count selects the occupancy-driven
-// kernels on the device).  Integer atomics only: the count is exact and order-independent.
+// kernels on the device) + occupancy bitmask (bit i of the flat voxel index i: the occupancy-driven forward finds
+// the non-zero voxels of a halo row with one 64-bit load instead of scanning the floats).  Integer atomics only: the
+// count is exact and order-independent.
 // (one atomic per CTA: thousands of same-address atomics at the end of the kernel were a visible serial tail)
 __device__ __forceinline__ void add_count(unsigned cnt, unsigned long long* nnz) {
     __shared__ unsigned s_cnt[8];
@@ -48,71 +50,113 @@ __device__ __forceinline__ void add_count(unsigned cnt, unsigned long long* nnz)
     }
 }
 
-__global__ void __launch_bounds__(256) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
-                                                          unsigned long long* nnz) {
-    // 4 x 16-byte loads in flight per thread (one per step left the pass at 0.73 of the HBM copy rate)
-    const long long n2 = n >> 1;
+// A lane holds NB occupancy bits of NB consecutive voxels (lane l of the warp: voxels [(wb + l) * NB, +NB)); the
+// 32 / NB lanes of a group assemble one 32-bit mask word by a butterfly OR and the group leader stores it.  Call with
+// the whole warp converged; wb = chunk index of lane 0 (a multiple of 32).
+template <int NB>
+__device__ __forceinline__ void store_mask_words(unsigned bits, long long wb, unsigned* __restrict__ mask, long long nw) {
+    constexpr int GL = 32 / NB;  // lanes per word
+    const int lane = threadIdx.x & 31;
+    unsigned v = bits << (NB * (lane % GL));
+#pragma unroll
+    for (int o = 1; o < GL; o <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane % GL == 0 && (wb + lane) / GL < nw) mask[(wb + lane) / GL] = v;  // nw = ceil(n / 32) words hold live bits
+}
+
+__global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
+                                                          unsigned long long* nnz, unsigned* __restrict__ mask) {
+    // 4 x 16-byte loads in flight per thread (one per step left the pass at 0.73 of the HBM copy rate).  Warp-uniform
+    // trip count (the mask words are assembled across lanes): a lane past the end contributes zeros.
+    const long long n2 = n >> 1;        // full pairs
+    const long long np = (n + 1) >> 1;  // pairs incl. the half pair of an odd n
+    const long long nw = (n + 31) >> 5;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     unsigned cnt = 0;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n2; i += 4 * stride) {
+    long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane);
+    for (; wb + 3 * stride + 32 <= n2; wb += 4 * stride) {  // all four steps are full for every lane of the warp
         double2 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const double2*>(in)[i + u * stride];
+        for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const double2*>(in)[wb + u * stride + lane];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float2 o = make_float2((float)v[u].x, (float)v[u].y);
-            reinterpret_cast<float2*>(out)[i + u * stride] = o;
-            cnt += (o.x != 0.f) + (o.y != 0.f);
+            reinterpret_cast<float2*>(out)[wb + u * stride + lane] = o;
+            const unsigned b = (o.x != 0.f ? 1u : 0u) | (o.y != 0.f ? 2u : 0u);
+            cnt += __popc(b);
+            store_mask_words<2>(b, wb + u * stride, mask, nw);
         }
     }
-    for (; i < n2; i += stride) {
-        const double2 v = reinterpret_cast<const double2*>(in)[i];
-        const float2 o = make_float2((float)v.x, (float)v.y);
-        reinterpret_cast<float2*>(out)[i] = o;
-        cnt += (o.x != 0.f) + (o.y != 0.f);
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        out[n - 1] = (float)in[n - 1];
-        cnt += out[n - 1] != 0.f;
+    for (; wb < np; wb += stride) {  // remaining steps, element-wise bounds
+        const long long i = wb + lane;
+        float2 o = make_float2(0.f, 0.f);
+        if (i < n2) {
+            const double2 v = reinterpret_cast<const double2*>(in)[i];
+            o = make_float2((float)v.x, (float)v.y);
+            reinterpret_cast<float2*>(out)[i] = o;
+        } else if (2 * i < n) {
+            o.x = (float)in[2 * i];
+            out[2 * i] = o.x;
+        }
+        const unsigned b = (o.x != 0.f ? 1u : 0u) | (o.y != 0.f ? 2u : 0u);
+        cnt += __popc(b);
+        store_mask_words<2>(b, wb, mask, nw);
     }
     add_count(cnt, nnz);
 }
 
 __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n,
-                                                         unsigned long long* nnz) {
-    const long long n16 = n >> 4;
+                                                         unsigned long long* nnz, unsigned* __restrict__ mask) {
+    const long long nc = (n + 15) >> 4;  // 16-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     unsigned cnt = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
-        float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
+        const long long i = wb + lane;
+        unsigned bits = 0;
+        if (16 * i + 15 < n) {
+            const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            float4* o = reinterpret_cast<float4*>(out) + 4 * i;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned b0 = w[k] & 0xffu, b1 = (w[k] >> 8) & 0xffu, b2 = (w[k] >> 16) & 0xffu, b3 = w[k] >> 24;
-            o[k] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
-            cnt += (b0 != 0) + (b1 != 0) + (b2 != 0) + (b3 != 0);
+            for (int k = 0; k < 4; ++k) {
+                const unsigned b0 = w[k] & 0xffu, b1 = (w[k] >> 8) & 0xffu, b2 = (w[k] >> 16) & 0xffu, b3 = w[k] >> 24;
+                o[k] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+                bits |= ((b0 != 0 ? 1u : 0u) | (b1 != 0 ? 2u : 0u) | (b2 != 0 ? 4u : 0u) | (b3 != 0 ? 8u : 0u)) << (4 * k);
+            }
+        } else {
+            for (long long j = 16 * i; j < n; ++j) {
+                const unsigned char b = in[j];
+                out[j] = (float)b;
+                bits |= (b != 0 ? 1u : 0u) << (int)(j - 16 * i);
+            }
         }
+        cnt += __popc(bits);
+        store_mask_words<16>(bits, wb, mask, (n + 31) >> 5);
     }
-    if (blockIdx.x == 0)
-        for (long long i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) {
-            out[i] = (float)in[i];
-            cnt += in[i] != 0;
-        }
     add_count(cnt, nnz);
 }
 
-__global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict__ in, long long n, unsigned long long* nnz) {
-    const long long n4 = n >> 2;
+__global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict__ in, long long n, unsigned long long* nnz,
+                                                        unsigned* __restrict__ mask) {
+    const long long nq = (n + 3) >> 2;  // 4-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     unsigned cnt = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = reinterpret_cast<const float4*>(in)[i];
-        cnt += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nq; wb += stride) {
+        const long long i = wb + lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * i + 3 < n) {
+            v = reinterpret_cast<const float4*>(in)[i];
+        } else {
+            if (4 * i < n) v.x = in[4 * i];
+            if (4 * i + 1 < n) v.y = in[4 * i + 1];
+            if (4 * i + 2 < n) v.z = in[4 * i + 2];
+        }
+        const unsigned bits = (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
+        cnt += __popc(bits);
+        store_mask_words<4>(bits, wb, mask, (n + 31) >> 5);
     }
-    if (blockIdx.x == 0)
-        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) cnt += in[i] != 0.f;
     add_count(cnt, nnz);
 }
 
@@ -170,6 +214,12 @@ extern "C" int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n,
 }
 
 
+extern "C" int64_t sn_grid_state_bytes(int64_t n) {
+    if (n < 0) return SN_ERR_BAD_ARG;
+    // count + ticket, one mask bit per voxel, 4 padding words (the forward reads word pairs), rounded to 16 bytes
+    return (16 + 4 * ((n + 31) / 32 + 4) + 15) & ~(int64_t)15;
+}
+
 extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream) {
     if (!x || !nnz || n < 0) return SN_ERR_BAD_ARG;
     if (dtype != SN_F32 && dtype != SN_F64 && dtype != SN_U8) return SN_ERR_BAD_ARG;
@@ -180,12 +230,13 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     cudaError_t e = cudaMemsetAsync(nnz, 0, 2 * sizeof(unsigned long long), s);  // [0] count, [1] ticket of the tap-gradient tail
     if (e != cudaSuccess) return sn::cuda_rc(e);
     if (n == 0) return SN_OK;
+    unsigned* mask = reinterpret_cast<unsigned*>(nnz + 2);  // occupancy bits follow the two counters (sn_grid_state_bytes)
     if (dtype == SN_F64)
-        sn::prepare_f64_kernel<<<sn::grid_for(n / 2 + 1, 256 * 4), 256, 0, s>>>((const double*)x, x32, n, nnz);
+        sn::prepare_f64_kernel<<<sn::grid_for(n / 2 + 1, 256 * 4), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
     else if (dtype == SN_U8)
-        sn::prepare_u8_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz);
+        sn::prepare_u8_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz, mask);
     else
-        sn::count_f32_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const float*)x, n, nnz);
+        sn::count_f32_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const float*)x, n, nnz, mask);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -82,27 +82,50 @@ __device__ __forceinline__ float g0_of(double p, double d) { return p > 0.0 ? (f
 // FP64 issue is scarce on B200: inside the FFMA-bound dense stencil this function costs +25 % (libm tanh(double):
 // +27 %; a variant with fewer FP64 operations but more selects / conversions: +38 %), so the dense stencil keeps
 // tanhf; the occupancy-driven kernel is not FP32-bound and pays +16 us at config 2 (profiles/r1_notes.md).
-// exp(2s) = 2^k * P(r), degree-11 Taylor on |r| <= ln2/2, then 1 - 2/(e + 1).
+// tanh(s) = (1 - t) / (1 + t) with t = exp(-2s) = 2^k * P(r): degree-10 Taylor on |r| <= ln2/2 (2e-13), the quotient
+// from the hardware reciprocal seed + two Newton steps (the first version, exp(2s) by a degree-11 polynomial and an
+// IEEE division, was 66 instructions per call and 40 % of all instructions of the occupancy-driven forward at
+// config 2 — ncu, profiles/r1_notes.md; this one is ~30).  Absolute error < 1e-12.
+// (coefficients in constant memory: as literals every one of them cost two uniform-register moves in front of its DFMA,
+// 22 of the function's 53 instructions)
+__constant__ double kTanhC[14] = {
+    1.4426950408889634,          // [0] log2(e)
+    -6.93147180369123816490e-01, // [1] -ln2 hi
+    -1.90821492927058770002e-10, // [2] -ln2 lo
+    2.7557319223985893e-07,      // [3] 1/10!
+    2.7557319223985888e-06,      // [4] 1/9!
+    2.4801587301587302e-05,      // [5] 1/8!
+    1.9841269841269841e-04,      // [6] 1/7!
+    1.3888888888888889e-03,      // [7] 1/6!
+    8.3333333333333332e-03,      // [8] 1/5!
+    4.1666666666666664e-02,      // [9] 1/4!
+    1.6666666666666666e-01,      // [10] 1/3!
+    0.5, 1.0, 20.0};
 __device__ __forceinline__ double tanh_pos_f64(double s) {
     if (s > 20.0) return 1.0;
-    const double x = s + s;
-    const double kf = rint(x * 1.4426950408889634);
-    const double r = fma(-kf, 6.93147180369123816490e-01, x) - kf * 1.90821492927058770002e-10;  // ln2 hi / lo
-    double p = 2.5052108385441720e-08;  // 1/11!
-    p = fma(p, r, 2.7557319223985888e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.4801587301587302e-05);
-    p = fma(p, r, 1.9841269841269841e-04);
-    p = fma(p, r, 1.3888888888888889e-03);
-    p = fma(p, r, 8.3333333333333332e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int k = (int)kf;
-    const double e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // p * 2^k, k in [0, 58]
-    return 1.0 - 2.0 / (e + 1.0);
+    const double x = -2.0 * s;
+    const double kf = rint(x * kTanhC[0]);
+    double r = fma(kf, kTanhC[1], x);
+    r = fma(kf, kTanhC[2], r);
+    double q = kTanhC[3];
+    q = fma(q, r, kTanhC[4]);
+    q = fma(q, r, kTanhC[5]);
+    q = fma(q, r, kTanhC[6]);
+    q = fma(q, r, kTanhC[7]);
+    q = fma(q, r, kTanhC[8]);
+    q = fma(q, r, kTanhC[9]);
+    q = fma(q, r, kTanhC[10]);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const int k = (int)kf;  // in [-58, 0]
+    const double t = __hiloint2double(__double2hiint(q) + k * 1048576, __double2loint(q));  // q * 2^k
+    const double d = 1.0 + t;  // in (1, 2]
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));  // ~20 bits
+    rc = fma(rc, fma(-d, rc, 1.0), rc);
+    rc = fma(rc, fma(-d, rc, 1.0), rc);
+    return (1.0 - t) * rc;
 }
 
 // Tail of the tap-gradient kernels: the CTA that draws the last ticket sums the partial rows of all CTAs in row order

@@ -23,15 +23,17 @@ int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // st
 // stencil_fwd_sparse.cu
 bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
-                      unsigned long long nnz_max, int B, int Z, int X, int Y, int kz, int kx, int ky, cudaStream_t stream);
+                      unsigned long long nnz_max, const unsigned* occ_mask, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                      cudaStream_t stream);
 }  // namespace sn
 
-// occupancy (percent of the voxels) up to which the occupancy-driven forward is selected (measured break-even,
-// scratch/time_sparse.py / profiles/r1_notes.md)
-// measured break-even on B200 (profiles/r1_notes.md, float64 predictions): (9,5,5) 1.3 %, (9,7,7) / 9^3 above 4 %
+// occupancy (percent of the voxels) up to which the occupancy-driven forward is selected: measured break-even on B200
+// with the mask-driven kernel and float64 predictions (scratch/occ_check.py, profiles/r1_notes.md): (9,5,5) on 64^3
+// 66 us at 1.6 %, 85 us at 3 %, 114 us at 5 % against 92 us dense; (9,7,7) 101 us at 1.6 % against 183 us; 9^3 on 128^3
+// 231 us against 571 us.  (The scanning kernel without the occupancy bits broke even at 1.3 %.)
 static unsigned long long fwd_sparse_nnz_max(long long nvox, int kx, int ky) {
     static const double forced = getenv("SN_SPARSE_FWD_PCT") ? atof(getenv("SN_SPARSE_FWD_PCT")) : -1.0;
-    const double pct = forced >= 0.0 ? forced : (kx * ky <= 32 ? 1.25 : 4.0);
+    const double pct = forced >= 0.0 ? forced : (kx * ky <= 64 ? 3.0 : 4.0);
     return (unsigned long long)((double)nvox * pct / 100.0);
 }
 
@@ -63,23 +65,25 @@ extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, in
     sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, nullptr, 0};
     cudaStream_t s = (cudaStream_t)stream;
     const bool sparse_ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
+    // sn_grid_prepare's state buffer: count, ticket, then one occupancy bit per voxel (sn_grid_state_bytes)
+    const unsigned* occ = nnz ? reinterpret_cast<const unsigned*>(nnz + 2) : nullptr;
     const unsigned long long nnz_max = fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky);
     if (mode == SN_PATH_SPARSE) {
         if (!sparse_ok) return SN_ERR_UNSUPPORTED;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
     }
     if (mode == SN_PATH_AUTO && sparse_ok && nnz) {
         // both kernels are enqueued; the non-zero count decides on the device which one works
         p.nnz = nnz; p.nnz_max = nnz_max;
         int rc = dense_fwd(p, ky, s);
         if (rc == SN_ERR_UNSUPPORTED)  // no dense instantiation for this width: the occupancy-driven kernel always runs
-            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
         if (rc) return rc;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, B, Z, X, Y, kz, kx, ky, s);
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, occ, B, Z, X, Y, kz, kx, ky, s);
     }
     int rc = dense_fwd(p, ky, s);
     if (rc == SN_ERR_UNSUPPORTED) {
-        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, B, Z, X, Y, kz, kx, ky, s);
+        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
         rc = sn::stencil_fwd_generic(p, ky, s);
     }
     return rc;

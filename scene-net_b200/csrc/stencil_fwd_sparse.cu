@@ -43,6 +43,8 @@ struct FsParams {
     int AS, RP;                 // accumulator plane: row pitch (floats), rows per plane
     int tiles_z, tiles_x, tiles_y, ntiles;
     unsigned ws_magic;          // ceil(2^24 / WS): f / WS == (f * ws_magic) >> 24 for f < 2^13
+    const unsigned* mask;       // occupancy bits of x by flat voxel index (sn_grid_prepare), nw words; fwd_occ_kernel only
+    int nw;
 };
 
 struct FsEntry {
@@ -262,6 +264,264 @@ fwd_sparse_kernel(const FsParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mask-driven variant (the one that runs when the caller hands over sn_grid_prepare's state buffer).
+//
+// ncu of the scanning kernel above at config 2 (profiles/r1_notes.md): 74 M warp instructions, issue slots 79 % busy —
+// bound by instruction issue, and 30 M of them were phase A (every halo voxel is looked at by ~3 tiles: 16-byte
+// loads, bounds tests, four ballots per load).  sn_grid_prepare now leaves one occupancy BIT per voxel next to the
+// count, so phase A of this kernel reads a halo row's 32-column chunks as funnel-shifted mask words (one lane per
+// (x-row, chunk) pair), gets list positions from a warp prefix sum of the popcounts and only touches x for the
+// voxels that are set.  Phase B walks two list entries per 16-byte load with hand-formed shared-memory addresses;
+// phase C's index arithmetic is hoisted out of the tile loop.  Same lists, fixed accumulation order, no atomics.
+constexpr int kFoPairIt = 3;  // (x-row, chunk) pairs per lane: HX * ceil((IY + ky - 1) / 32) <= 96
+
+// acc[addr] += v * k for the lanes with ok != 0 (predicated: no branch, the warp stays converged)
+__device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .f32 t;\n\t"
+        "setp.ne.s32 q, %3, 0;\n\t"
+        "@q ld.shared.f32 t, [%0];\n\t"
+        "@q fma.rn.f32 t, %1, %2, t;\n\t"
+        "@q st.shared.f32 [%0], t;\n\t}" ::"r"(addr),
+        "f"(v), "f"(k), "r"(ok)
+        : "memory");
+}
+
+template <int NI2, bool OUT64>
+__global__ void __launch_bounds__(kFsThreads, NI2 <= 2 ? 4 : 3)
+fwd_occ_kernel(const FsParams p) {
+    if (p.nnz && *p.nnz > p.nnz_max) return;  // dense input: stencil_fwd_kernel does the work
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int plane_floats = p.RP * p.AS;
+    const int P = p.kx * p.ky, T = p.kz * P;
+    float* acc = reinterpret_cast<float*>(smem_raw);
+    const int acc_floats = (kRZ * plane_floats + p.kx * p.AS + 31) & ~31;
+    FsEntry* lists = reinterpret_cast<FsEntry*>(acc + acc_floats);  // [HZ][kFsCap]
+    float* sk = reinterpret_cast<float*>(lists + p.HZ * kFsCap);
+    int* cnt = reinterpret_cast<int*>(sk + ((T + 31) & ~31));        // [HZ] non-zeros per halo z-row
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    for (int t = tid; t < T; t += kFsThreads) sk[t] = __ldg(p.Kstar + t);
+
+    // phase A constants of this lane: its (x-row, 32-column chunk) pair in each iteration
+    // (flat voxel indices fit 32 bits: the launcher only picks this kernel below 2^31 - 2^20 voxels)
+    const int ply = p.pla - p.off;
+    const int HW = p.IY + p.ky - 1;
+    const int nwc = (HW + 31) >> 5;
+    const int npairs = p.HX * nwc;
+    int pux[kFoPairIt], pc0[kFoPairIt], poff[kFoPairIt], pbase[kFoPairIt];
+#pragma unroll
+    for (int i = 0; i < kFoPairIt; ++i) {
+        const int pr = 32 * i + lane;
+        pux[i] = pr < npairs ? pr / nwc : -1;
+        pc0[i] = pr < npairs ? (pr - pux[i] * nwc) * 32 : 0;
+        poff[i] = pux[i] * p.Y + pc0[i];                                     // voxel offset from the halo row's origin
+        pbase[i] = ((pux[i] + p.kx - 1) * p.AS + pc0[i] + (p.ky - 1)) << 2;  // accumulator byte offset of bit 0
+    }
+    const int zstep = p.X * p.Y;
+    // phase B: lane -> plane taps t' = 32 j + lane (t' = dx * ky + dy)
+    float* accp = acc + warp * plane_floats;  // this warp's output plane (zo = warp)
+    uint32_t accl[NI2];  // shared-memory byte address of this lane's accumulator for an entry with base 0
+    int okp[NI2];
+#pragma unroll
+    for (int j = 0; j < NI2; ++j) {
+        const int tp = 32 * j + lane;
+        okp[j] = tp < P ? 1 : 0;
+        const int tq = okp[j] ? tp : 0;
+        accl[j] = smem_u32(accp) - 4u * (uint32_t)((tq / p.ky) * p.AS + (tq % p.ky));
+    }
+    const uint32_t lists_w = smem_u32(lists + warp * kFsCap);  // list of halo z-row `warp` (dz = 0)
+    const float* skl = sk + lane;
+    // phase C: lane -> four 4-voxel groups of the 8 x IX x IY tile's plane (IX * IY == 512)
+    const int groups_y = p.IY >> 2;
+    int exy[4];  // xo | yo << 16
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int g = lane + 32 * i;
+        exy[i] = (g / groups_y) | (((g % groups_y) << 2) << 16);
+    }
+    const bool vec = (p.Y & 3) == 0;
+    __syncthreads();
+
+    // tile coordinates advance by the (decoded) grid stride with carries: no divisions inside the tile loop
+    int tc[4], ts[4];  // ty, tx, tz, b of the current tile / of the stride G
+    {
+        int t = blockIdx.x, g = G;
+        tc[0] = t % p.tiles_y; t /= p.tiles_y; ts[0] = g % p.tiles_y; g /= p.tiles_y;
+        tc[1] = t % p.tiles_x; t /= p.tiles_x; ts[1] = g % p.tiles_x; g /= p.tiles_x;
+        tc[2] = t % p.tiles_z; tc[3] = t / p.tiles_z; ts[2] = g % p.tiles_z; ts[3] = g / p.tiles_z;
+    }
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += G) {
+        const int b = tc[3], z0 = tc[2] * kRZ, x0 = tc[1] * p.IX, y0 = tc[0] * p.IY;
+        {
+            tc[0] += ts[0];
+            int cy = tc[0] >= p.tiles_y ? 1 : 0;
+            tc[0] -= cy ? p.tiles_y : 0;
+            tc[1] += ts[1] + cy;
+            cy = tc[1] >= p.tiles_x ? 1 : 0;
+            tc[1] -= cy ? p.tiles_x : 0;
+            tc[2] += ts[2] + cy;
+            cy = tc[2] >= p.tiles_z ? 1 : 0;
+            tc[2] -= cy ? p.tiles_z : 0;
+            tc[3] += ts[3] + cy;
+        }
+        {
+            float4* a4 = reinterpret_cast<float4*>(accp);
+            for (int i = lane; i < (plane_floats >> 2); i += 32) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // live halo columns of this tile (gy = y0 - ply + c inside [0, Y)) and live x-rows, per pair of this lane
+        unsigned vm[kFoPairIt];
+        {
+            const int c_lo = max(0, ply - y0), c_hi = min(HW, p.Y - y0 + ply);
+#pragma unroll
+            for (int i = 0; i < kFoPairIt; ++i) {
+                const int gx = x0 - p.plx + pux[i];
+                const int a = min(max(c_lo - pc0[i], 0), 32), e = min(max(c_hi - pc0[i], 0), 32);
+                vm[i] = (pux[i] >= 0 && gx >= 0 && gx < p.X && e > a) ? ((0xffffffffu >> (32 - (e - a))) << a) : 0u;
+            }
+        }
+        // flat index of the halo box origin (z-row 0, x-row 0, column 0); may be negative at the grid's first rows
+        const int org = ((b * p.Z + (z0 - p.plz)) * p.X + (x0 - p.plx)) * p.Y + (y0 - ply);
+        int lo = 0;
+        while (true) {
+            // ---- A: list the non-zero voxels [lo, lo + cap) of every halo z-row from the occupancy bits
+            bool my_more = false;
+            for (int zr = warp; zr < p.HZ; zr += kFsWarps) {
+                FsEntry* lst = lists + zr * kFsCap;
+                const int gz = z0 - p.plz + zr;
+                const bool z_ok = gz >= 0 && gz < p.Z;
+                int n = 0;
+#pragma unroll
+                for (int i = 0; i < kFoPairIt; ++i) {
+                    if (32 * i >= npairs) break;  // warp-uniform
+                    unsigned m = 0u;
+                    const int bit0 = org + zr * zstep + poff[i];
+                    if (z_ok && vm[i]) {
+                        const int wi = bit0 >> 5;  // floor
+                        const unsigned w0 = (unsigned)wi < (unsigned)p.nw ? __ldg(p.mask + wi) : 0u;
+                        const unsigned w1 = (unsigned)(wi + 1) < (unsigned)p.nw ? __ldg(p.mask + wi + 1) : 0u;
+                        m = __funnelshift_r(w0, w1, (unsigned)bit0 & 31u) & vm[i];
+                    }
+                    const int c = __popc(m);
+                    int incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    int pos = n + incl - c - lo;
+                    while (m) {
+                        const int bp = __ffs(m) - 1;
+                        m &= m - 1u;
+                        if (pos >= 0 && pos < kFsCap) {
+                            FsEntry en;
+                            en.val = __ldg(p.x + (bit0 + bp));
+                            en.base = pbase[i] + (bp << 2);  // byte offset inside the plane
+                            lst[pos] = en;
+                        }
+                        ++pos;
+                    }
+                    n += total;
+                }
+                if (lane == 0) {
+                    cnt[zr] = n;
+                    // phase B walks the list two entries at a time: an odd list gets a no-op entry (value 0 at the
+                    // accumulators of halo voxel (0, 0): inside this warp's own plane for every tap)
+                    const int nl = n - lo;
+                    if (nl > 0 && nl < kFsCap && (nl & 1)) {
+                        FsEntry en;
+                        en.val = 0.f;
+                        en.base = ((p.kx - 1) * p.AS + (p.ky - 1)) << 2;
+                        lst[nl] = en;
+                    }
+                }
+                my_more |= n > lo + kFsCap;
+            }
+            const int more = __syncthreads_or(my_more ? 1 : 0);
+            // ---- B: warp zo adds slice dz of the taps at every listed voxel of row zo + dz
+            for (int dz = 0; dz < p.kz; ++dz) {
+                int n = cnt[warp + dz] - lo;
+                n = n < 0 ? 0 : (n > kFsCap ? kFsCap : n);
+                if (n == 0) continue;
+                float kk[NI2];
+#pragma unroll
+                for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[dz * P + 32 * j] : 0.f;
+                // two list entries per 16-byte broadcast load; shared-memory addresses are formed by hand (the generic
+                // C++ form cost 12 instructions per entry, this one 5) and the read-modify-write is predicated, not
+                // branched, so the warp stays converged: its LDS / STS are executed in program order, which is what
+                // makes an entry see the sums its predecessor stored from OTHER lanes
+                __syncwarp();
+                uint32_t la = lists_w + (uint32_t)dz * (kFsCap * 8u);
+                const uint32_t lend = la + (((uint32_t)n + 1u) >> 1) * 16u;
+#pragma unroll 1
+                for (; la != lend; la += 16u) {
+                    float v0, v1;
+                    uint32_t b0, b1;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=r"(b0), "=f"(v1), "=r"(b1) : "r"(la) : "memory");
+#pragma unroll
+                    for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b0, v0, kk[j], okp[j]);
+#pragma unroll
+                    for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b1, v1, kk[j], okp[j]);
+                }
+            }
+            if (!more) break;
+            __syncthreads();  // the lists are rewritten by the next round
+            lo += kFsCap;
+        }
+        // ---- C: epilogue of this warp's plane (lane -> 4 consecutive y)
+        {
+            const int gz = z0 + warp;
+            const size_t idx0 = (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xo = exy[i] & 0xffff, yo = exy[i] >> 16;
+                const int gx = x0 + xo, gy = y0 + yo;
+                if (gz >= p.Z || gx >= p.X || gy >= p.Y) continue;
+                const float* a = accp + (xo + p.kx - 1) * p.AS + yo + (p.ky - 1);
+                const size_t idx = idx0 + (size_t)xo * p.Y + yo;
+                const int ny = p.Y - gy;
+                if constexpr (OUT64) {  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
+                    double od[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float s = a[r];
+                        od[r] = s > 0.f ? tanh_pos_f64((double)s) : 0.0;
+                    }
+                    double* out = reinterpret_cast<double*>(p.pred) + idx;
+                    if (vec) {
+                        reinterpret_cast<double2*>(out)[0] = make_double2(od[0], od[1]);
+                        reinterpret_cast<double2*>(out)[1] = make_double2(od[2], od[3]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (r < ny) out[r] = od[r];
+                    }
+                } else {
+                    float o[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float s = a[r];
+                        o[r] = s > 0.f ? tanhf(s) : 0.f;
+                    }
+                    float* out = reinterpret_cast<float*>(p.pred) + idx;
+                    if (vec) {
+                        *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (r < ny) out[r] = o[r];
+                    }
+                }
+            }
+        }
+        __syncthreads();  // lists and counts are rewritten by the next tile
+    }
+}
+
 // geometry; false when the kernel does not cover the shape (caller uses the dense stencil)
 static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, FsParams& p, size_t& smem, int& ni2) {
     p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx; p.ky = ky;
@@ -308,7 +568,11 @@ bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky) {
 
 template <int NI2>
 static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
-    auto kern = fwd_sparse_kernel<NI2>;
+    // the mask-driven kernel needs the occupancy bits, at most kFoPairIt * 32 (x-row, chunk) pairs per halo z-row and
+    // 32-bit flat voxel indices (incl. the halo overshoot)
+    const bool occ = p.mask && p.HX * ((p.IY + p.ky - 1 + 31) >> 5) <= kFoPairIt * 32 && p.IX * p.IY == 512 &&
+                     (long long)p.B * p.Z * p.X * p.Y < (1ll << 31) - (1ll << 20);
+    auto kern = occ ? (p.out_f64 ? fwd_occ_kernel<NI2, true> : fwd_occ_kernel<NI2, false>) : fwd_sparse_kernel<NI2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -320,13 +584,20 @@ static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
 }
 
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
-                      unsigned long long nnz_max, int B, int Z, int X, int Y, int kz, int kx, int ky, cudaStream_t stream) {
+                      unsigned long long nnz_max, const unsigned* occ_mask, int B, int Z, int X, int Y, int kz, int kx, int ky,
+                      cudaStream_t stream) {
     FsParams p{};
     size_t smem;
     int ni2;
     if (!plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2)) return SN_ERR_UNSUPPORTED;
     p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = nnz; p.nnz_max = nnz_max;
     p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
+    {
+        static const bool no_mask = getenv("SN_FWD_NO_MASK") != nullptr;  // measurement: force the scanning kernel
+        p.mask = no_mask ? nullptr : occ_mask;
+        const long long nw = ((long long)B * Z * X * Y + 31) >> 5;
+        p.nw = nw < (1ll << 30) ? (int)nw : 0;
+    }
     if ((uintptr_t)x & 15) return SN_ERR_ALIGN;
     switch (ni2) {
         case 1: return launch_fs<1>(p, smem, stream);

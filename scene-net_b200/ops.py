@@ -7,13 +7,14 @@ and raises otherwise — there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import torch
 
 from . import _lib
-from ._lib import SN_F32, SN_F64, SN_U8, ModelDesc, check, lib
+from ._lib import SN_F32, SN_F64, SN_I32, SN_I64, SN_U8, ModelDesc, check, lib
 
 _DT = {torch.float32: SN_F32, torch.float64: SN_F64}
 
@@ -224,10 +225,17 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@functools.lru_cache(maxsize=64)
+def _state_words(n: int) -> int:
+    return int(lib.sn_grid_state_bytes(n)) // 8
+
+
 def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
-    (x itself for float32 input), nnz a 2-element int64 device tensor ([0] = number of non-zero voxels): the
-    forward and the backward use it ON THE DEVICE to pick the occupancy-driven kernels for sparse grids.
+    (x itself for float32 input), nnz the grid state buffer as an int64 device tensor ([0] = number of non-zero
+    voxels, [1] = ticket counter of the backward, then one occupancy bit per voxel): the forward and the backward use
+    the count ON THE DEVICE to pick the occupancy-driven kernels for sparse grids, and the occupancy-driven forward
+    finds the non-zero voxels through the bits.
     stream: run the pass on this (side) stream after everything enqueued so far on the current one; the outputs
     are allocated on the current stream and the caller joins the streams (`current.wait_stream(stream)`)."""
     _need_cuda(x, "x")
@@ -241,7 +249,7 @@ def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     x32 = x if x.dtype == torch.float32 else torch.empty(x.shape, dtype=torch.float32, device=x.device)
     if x.numel() == 0:
         return x32, torch.zeros(2, dtype=torch.int64, device=x.device)
-    nnz = torch.empty(2, dtype=torch.int64, device=x.device)  # [0] non-zero count, [1] ticket counter of the backward
+    nnz = torch.empty(_state_words(x.numel()), dtype=torch.int64, device=x.device)
     dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
     with _on_device(x.device):
         if stream is not None:
@@ -435,6 +443,41 @@ def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
     with _on_device(p.device):
         check(lib.sn_threshold(p.data_ptr(), _DT[p.dtype], float(tau), p.numel(), out.data_ptr(), _stream()), "sn_threshold")
     return out
+
+
+_YDT = {torch.float32: SN_F32, torch.float64: SN_F64, torch.uint8: SN_U8, torch.int32: SN_I32, torch.int64: SN_I64}
+
+
+def confusion_counts(pred: torch.Tensor, y: torch.Tensor, tau: float, total: Optional[torch.Tensor] = None,
+                     batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """{TP, FP, TN, FN} of (pred >= tau) against (y != 0) in one pass (sn_confusion_counts): returns this call's counts
+    as an int64 [4] device tensor (`batch`, overwritten when given) and ADDS them to `total` (int64 [4]) when given."""
+    _need_cuda(pred, "pred")
+    _need_cuda(y, "y")
+    if pred.dtype not in _DT:
+        raise TypeError(f"confusion_counts: float32/float64 predictions only, got {pred.dtype}")
+    if y.dtype == torch.bool:
+        y = y.view(torch.uint8)
+    if y.dtype not in _YDT:
+        raise TypeError(f"confusion_counts: unsupported target dtype {y.dtype}")
+    if pred.numel() != y.numel():
+        raise ValueError(f"confusion_counts: {pred.numel()} predictions vs {y.numel()} targets")
+    pred, y = pred.contiguous(), y.contiguous()
+    if pred.data_ptr() % 16:
+        pred = pred.clone()
+    if y.data_ptr() % 16:
+        y = y.clone()
+    if batch is None:
+        batch = torch.empty(4, dtype=torch.int64, device=pred.device)
+    for t, name in ((batch, "batch"), (total, "total")):
+        if t is not None and (t.dtype != torch.int64 or t.numel() != 4 or not t.is_contiguous() or t.device != pred.device):
+            raise ValueError(f"confusion_counts: `{name}` must be a contiguous int64 [4] tensor on {pred.device}")
+    if pred.numel() == 0:  # nothing to count (an empty tensor has no address to hand over)
+        return batch.zero_()
+    with _on_device(pred.device):
+        check(lib.sn_confusion_counts(pred.data_ptr(), _DT[pred.dtype], y.data_ptr(), _YDT[y.dtype], pred.numel(), float(tau),
+                                      batch.data_ptr(), _ptr(total), _stream()), "sn_confusion_counts")
+    return batch
 
 
 def fp32_peak_probe(iters: int = 2000, device=None) -> float:

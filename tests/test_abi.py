@@ -35,16 +35,18 @@ def test_argument_validation_without_gpu():
     assert lib.sn_scenenet_bwd_workspace_bytes(0, 8, 8, 8, 3, 3, 3) == -1
     assert lib.sn_scenenet_bwd_workspace_bytes(32, 64, 64, 64, 9, 5, 5) > 0
     assert lib.sn_grid_prepare(None, 1, 8, None, None, None) == -1
+    assert lib.sn_grid_state_bytes(-1) == -1 and lib.sn_grid_state_bytes(0) == 32 and lib.sn_grid_state_bytes(1 << 23) == 16 + (1 << 20) + 16
+    assert lib.sn_confusion_counts(None, 1, None, 3, 8, 0.65, None, None, None) == -1
     assert lib.sn_scenenet_tapgrad(None, None, None, 0, 1, 8, 8, 8, 3, 3, 3, None, None, 0, None) == -1
     assert lib.sn_criterion_workspace_bytes(0) == -1 and lib.sn_criterion_workspace_bytes(1 << 23) > 0
     assert lib.sn_criterion_fwd(None, None, 1, 8, None, None, 10, 1.0, 2.0, 1.0, 4.0, 1e-6, 3, None, None, None, 0, None) == -1
     assert lib.sn_param_penalty(None, None, 0, 5.0, None, None) == -1
     assert lib.sn_peer_allreduce_buffer_bytes(8) == 2 * 8 * 128 * 4 and lib.sn_peer_allreduce_buffer_bytes(17) == -1
     assert lib.sn_peer_allreduce(None, 13, 0, 2, None, None, None, None) == -1
-    # the selection rule of the AUTO modes (host-side query): config 2 at 1.6 % -> dense forward, occupancy-driven backward
+    # the selection rule of the AUTO modes (host-side query): config 2 at 1.6 % -> occupancy-driven forward and backward
     n = int(0.016 * 32 * 64 ** 3)
-    assert lib.sn_select_path(0, n, 32, 64, 64, 64, 9, 5, 5) == 1 and lib.sn_select_path(1, n, 32, 64, 64, 64, 9, 5, 5) == 2
-    assert lib.sn_select_path(0, n // 2, 32, 64, 64, 64, 9, 5, 5) == 2          # emptier grids: occupancy-driven forward
+    assert lib.sn_select_path(0, n, 32, 64, 64, 64, 9, 5, 5) == 2 and lib.sn_select_path(1, n, 32, 64, 64, 64, 9, 5, 5) == 2
+    assert lib.sn_select_path(0, 3 * n, 32, 64, 64, 64, 9, 5, 5) == 1           # 4.8 % occupied: dense forward
     assert lib.sn_select_path(1, 20 * n, 32, 64, 64, 64, 9, 5, 5) == 1          # 32 % occupied: dense tap gradient
     assert lib.sn_select_path(0, n, 8, 128, 128, 128, 9, 9, 9) == 2 and lib.sn_select_path(0, n, 8, 128, 128, 128, 15, 15, 15) == 1
 

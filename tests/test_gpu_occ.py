@@ -1,0 +1,79 @@
+"""GPU: the grid state buffer of sn_grid_prepare (count + one occupancy bit per voxel, ABI v3) and the mask-driven
+occupancy forward (fwd_occ_kernel in csrc/stencil_fwd_sparse.cu) against the dense stencil, the scanning variant and a
+float64 torch convolution."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from scenenet_b200 import ops
+    return ops
+
+
+def _bits(state, n):
+    w = state[2:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
+    return np.unpackbits(w.view("uint8"), bitorder="little")[:n]
+
+
+def _same_conv(x, K):
+    kz, kx, ky = K.shape
+    pad = []
+    for k in (ky, kx, kz):  # F.pad wants the last dimension first
+        pad += [(k - 1) // 2, k - 1 - (k - 1) // 2]
+    return F.conv3d(F.pad(x.double(), pad), K.double()[None, None])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1, 1), (2, 1, 7, 9, 13), (1, 1, 5, 3, 33), (3, 1, 20, 33, 70), (1, 1, 33, 31, 100),
+                                   (2, 1, 64, 64, 64), (1, 1, 3, 5, 257)])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32, torch.uint8])
+def test_prepare_state_bits(shape, dt):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(sum(shape))
+    for dens in (0.0, 0.03, 0.6, 1.0):
+        occ = torch.rand(shape, generator=g, device=DEV) < dens
+        x = occ.to(torch.uint8) if dt == torch.uint8 else (occ * (0.25 + torch.rand(shape, generator=g, device=DEV))).to(dt)
+        x32, st = ops.prepare(x)
+        n = x.numel()
+        ref = (x != 0).flatten().cpu().numpy().astype("uint8")
+        assert int(st[0]) == int(ref.sum()) and int(st[1]) == 0
+        assert np.array_equal(_bits(st, n), ref)
+        assert torch.equal(x32, x.float())
+
+
+@pytest.mark.parametrize("shape,ks", [((3, 1, 20, 33, 70), (9, 5, 5)), ((2, 1, 64, 64, 64), (9, 5, 5)), ((2, 1, 24, 40, 128), (9, 7, 7)),
+                                      ((1, 1, 33, 31, 100), (4, 6, 5)), ((1, 1, 40, 40, 40), (9, 9, 9)), ((2, 1, 9, 17, 31), (6, 5, 5)),
+                                      ((1, 1, 64, 64, 256), (9, 5, 5)), ((1, 1, 48, 48, 48), (11, 11, 11))])
+@pytest.mark.parametrize("odt", [torch.float64, torch.float32])
+def test_mask_driven_forward(shape, ks, odt):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(sum(shape) + sum(ks))
+    for dens in (0.0, 0.02, 0.3):
+        x = ((torch.rand(shape, generator=g, device=DEV) < dens) * torch.rand(shape, generator=g, device=DEV)).to(torch.float64)
+        K = torch.randn(ks, generator=g, device=DEV) * 0.2
+        x32, st = ops.prepare(x)
+        dense = ops.scenenet_fwd(x32, K, odt, mode=1)
+        mask = ops.scenenet_fwd(x32, K, odt, nnz=st, mode=2)
+        scan = ops.scenenet_fwd(x32, K, odt, mode=2)
+        want = torch.relu(torch.tanh(_same_conv(x32, K)))
+        for name, got in (("dense", dense), ("mask", mask), ("scan", scan)):
+            err = float((got.double() - want).abs().max())
+            assert err < 6e-6, (name, dens, err)  # float32 accumulation of up to 1331 taps
+        # capacity overflow rounds (rows with more than 128 non-zeros) are exercised by dens = 0.3
+
+
+def test_float64_tanh_of_the_occupancy_forward():
+    """identity kernel: pred = tanh(x) for x > 0, evaluated in float64 by tanh_pos_f64 (abs error < 1e-11)"""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    scale = torch.tensor([1e-4, 1e-2, 1.0, 12.0, 25.0, 0.3, 3.0, 0.05], device=DEV).repeat(8)
+    x = (torch.rand((2, 1, 16, 16, 64), generator=g, device=DEV) * scale).float()
+    K = torch.zeros((3, 3, 3), device=DEV)
+    K[1, 1, 1] = 1.0
+    x32, st = ops.prepare(x)
+    pred = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=2)
+    assert float((pred - torch.tanh(x.double())).abs().max()) < 1e-11
