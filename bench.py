@@ -177,6 +177,26 @@ def voxel_bench(device, hbm_gbs):
     out["batch_32x60k_pts_64^3"] = {"Mpts_per_s": 32 * 60_000 / dtg / 1e6, "clouds_per_s": 32 / dtg, "us": dtg * 1e6,
                                     "algorithmic_GBps": alg / dtg / 1e9, "hbm_frac": alg / dtg / 1e9 / hbm_gbs,
                                     "eager_us": dt * 1e6, "eager_clouds_per_s": 32 / dt}
+    # the batched device loader (core/datasets/ts40k.py): 8 batches of 32 in-memory [60000, 4] float64 samples -> pinned staging
+    # -> H2D on a copy stream -> one voxelize_clouds call per batch -> (x, y) float64 [32,1,64,64,64]; wall clock, host included
+    try:
+        import time
+        from scenenet_b200 import TS40KDeviceLoader
+        host_rows = [rows[i * 60_000:(i + 1) * 60_000].cpu().numpy() for i in range(32)] * 8
+        loader = TS40KDeviceLoader(host_rows, batch_size=32, device=device)
+        for _ in loader:  # warm-up epoch: pinned buffers allocated
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nb = 0
+        for x_, y_ in loader:
+            nb += x_.shape[0]
+        torch.cuda.synchronize()
+        dtl = time.perf_counter() - t0
+        out["device_loader_32x60k_pts_64^3"] = {"clouds_per_s": nb / dtl, "Mpts_per_s": nb * 60_000 / dtl / 1e6, "h2d_bytes_per_batch": 32 * 60_000 * 32,
+                                                "note": "wall clock over 8 batches incl. host staging into pinned memory and the H2D copy (PCIe / host-memcpy bound)"}
+    except Exception as e:  # noqa: BLE001
+        out["device_loader_32x60k_pts_64^3"] = {"error": repr(e)}
     out["note"] = ("6 launches per call (bounding box, edges, grid init, binning, finalize), timed as CUDA-graph replays of the "
                    "captured call (eager figures beside them are host-bound); algorithmic bytes = 56 B/point + 24 B/voxel (SURVEY 8d)")
     return out

@@ -8,6 +8,7 @@ from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is n
 from . import ops, voxel_ops, dist  # noqa: F401
 from .core.models.SCENE_Net import GENEO_Layer, SCENE_Net, SceneNet, SCENENetQuantile, SCENE_Net_Class  # noqa: F401
 from .core.datasets.torch_transforms import Voxelization, ToTensor, ToFullDense  # noqa: F401
+from .core.datasets.ts40k import TS40K, TS40KDeviceLoader  # noqa: F401
 from .core.criterions.geneo_loss import GENEO_Loss, GENEO_Tversky_Loss  # noqa: F401
 from .core.criterions.w_mse import WeightedMSE  # noqa: F401
 from .core.criterions.tversky_loss import FocalTverskyLoss, TverskyLoss  # noqa: F401

@@ -29,8 +29,12 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active"]
-for rep, name in [(f"gpurun_out/prof_r1_step.ncu-rep", f"{tag}_ncu_step_kernels.csv"), ("gpurun_out/prof_fsparse_r1.ncu-rep", f"{tag}_ncu_fwd_sparse.csv"),
-                  ("gpurun_out/prof_bin_r1.ncu-rep", f"{tag}_ncu_vox_bin.csv")]:
+REPS = {"r1b": [("gpurun_out/prof_r1_step.ncu-rep", "r1b_ncu_step_kernels.csv"), ("gpurun_out/prof_fsparse_r1.ncu-rep", "r1b_ncu_fwd_sparse.csv"),
+                ("gpurun_out/prof_bin_r1.ncu-rep", "r1b_ncu_vox_bin.csv")],
+        # third part of the round: mask-driven occupancy forward (1.6 % and empty grids), scanning kernel before it, prepare with the bit mask
+        "r1c": [("gpurun_out/prof_fo_r1f.ncu-rep", "r1c_ncu_fwd_occ.csv"), ("gpurun_out/prof_fo0_r1d.ncu-rep", "r1c_ncu_fwd_occ_empty_grids.csv"),
+                ("gpurun_out/prof_fs_r1c.ncu-rep", "r1c_ncu_fwd_scan_before.csv"), ("gpurun_out/prof_prep_r1d.ncu-rep", "r1c_ncu_prepare.csv")]}
+for rep, name in REPS.get(tag, []):
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
