@@ -743,6 +743,14 @@ def main():
                         "sample": "2 of the 32 grids, 1 warm-up + 3 timed fwd+bwd steps of the oracle port (float64 conv3d + autograd)"}
 
     if rank == 0:
+        if roof is not None:
+            # t_roof = max(4 T V B / P_fp32, 20 V B / BW_hbm) for one fwd + bwd step of the minimal-work dense
+            # formulation; the step reaches a larger share of it than the dense stencils could (0.55 / 0.52) because the
+            # occupancy-driven kernels do not execute the multiply-adds of empty voxels
+            t_step = total_ms / args.steps * 1e-3
+            t_fp32, t_hbm = 2 * fl / (roof["fp32_peak_tflops"] * 1e12), 20.0 * V / (hbm_gbs * 1e9)
+            roof["step_vs_survey_8d_roofline"] = {"t_roof_us": max(t_fp32, t_hbm) * 1e6, "t_fp32_us": t_fp32 * 1e6, "t_hbm_us": t_hbm * 1e6,
+                                                  "t_measured_us": t_step * 1e6, "frac": max(t_fp32, t_hbm) / t_step}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -101,8 +101,10 @@ __constant__ double kTanhC[14] = {
     4.1666666666666664e-02,      // [9] 1/4!
     1.6666666666666666e-01,      // [10] 1/3!
     0.5, 1.0, 20.0};
+// Branch-free (s is clamped to [0, 20]: tanh(0) comes out as exactly 0, tanh(20) as 1 to the last bit), so the four calls
+// of a row segment interleave their dependent DFMA chains instead of running one after the other.
 __device__ __forceinline__ double tanh_pos_f64(double s) {
-    if (s > 20.0) return 1.0;
+    s = fmin(fmax(s, 0.0), 20.0);
     const double x = -2.0 * s;
     const double kf = rint(x * kTanhC[0]);
     double r = fma(kf, kTanhC[1], x);

@@ -336,13 +336,7 @@ fwd_occ_kernel(const FsParams p) {
     const uint32_t lists_w = smem_u32(lists + warp * kFsCap);  // list of halo z-row `warp` (dz = 0)
     const float* skl = sk + lane;
     // phase C: lane -> four 4-voxel groups of the 8 x IX x IY tile's plane (IX * IY == 512)
-    const int groups_y = p.IY >> 2;
-    int exy[4];  // xo | yo << 16
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int g = lane + 32 * i;
-        exy[i] = (g / groups_y) | (((g % groups_y) << 2) << 16);
-    }
+    const int lg_gy = p.IY == 64 ? 4 : 3;  // 4-voxel groups per plane row: IY / 4 = 16 or 8
     const bool vec = (p.Y & 3) == 0;
     __syncthreads();
 
@@ -476,20 +470,25 @@ fwd_occ_kernel(const FsParams p) {
         {
             const int gz = z0 + warp;
             const size_t idx0 = (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 4; ++i) {
-                const int xo = exy[i] & 0xffff, yo = exy[i] >> 16;
+                const int g = lane + 32 * i;
+                const int xo = g >> lg_gy, yo = (g & ((1 << lg_gy) - 1)) << 2;
                 const int gx = x0 + xo, gy = y0 + yo;
                 if (gz >= p.Z || gx >= p.X || gy >= p.Y) continue;
                 const float* a = accp + (xo + p.kx - 1) * p.AS + yo + (p.ky - 1);
                 const size_t idx = idx0 + (size_t)xo * p.Y + yo;
                 const int ny = p.Y - gy;
                 if constexpr (OUT64) {  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
-                    double od[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float s = a[r];
-                        od[r] = s > 0.f ? tanh_pos_f64((double)s) : 0.0;
+                    double od[4] = {0.0, 0.0, 0.0, 0.0};
+                    const float s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3];
+                    // the four evaluations are branch-free and interleave; a warp whose 128 sums are all <= 0 (empty
+                    // regions of a scene) skips them
+                    if (__any_sync(__activemask(), fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > 0.f)) {
+                        od[0] = tanh_pos_f64((double)s0);  // relu inside: negative sums clamp to 0
+                        od[1] = tanh_pos_f64((double)s1);
+                        od[2] = tanh_pos_f64((double)s2);
+                        od[3] = tanh_pos_f64((double)s3);
                     }
                     double* out = reinterpret_cast<double*>(p.pred) + idx;
                     if (vec) {
