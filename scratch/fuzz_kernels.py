@@ -30,8 +30,16 @@ for it in range(n):
                 outs["sparse"] = ops.scenenet_fwd(x, K, od, mode=2)
             except Exception as e:
                 if "UNSUPPORTED" not in str(e): raise
-            x32, nnz = ops.prepare(x)
+            # grid state from a float64 / float32 hand-over in turn (count + occupancy bits): device-selected kernel and
+            # the mask-driven kernel forced at any occupancy
+            x32, nnz = ops.prepare(x.double() if it % 2 else x)
+            if int(nnz[0]) != int((x != 0).sum()):
+                bad += 1; print("COUNT MISMATCH", tag, flush=True)
             outs["auto"] = ops.scenenet_fwd(x32, K, od, nnz=nnz)
+            try:
+                outs["mask"] = ops.scenenet_fwd(x32, K, od, nnz=nnz, mode=2)
+            except Exception as e:
+                if "UNSUPPORTED" not in str(e): raise
             for name, p in outs.items():
                 err = (p.double() - p_ref).abs(); tol = 4e-6 * s_abs + 2e-7
                 if not bool((err <= tol).all()):
