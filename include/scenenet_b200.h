@@ -129,7 +129,8 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
  *   nnz   DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count + occupancy bits), or NULL
  *   mode  SN_PATH_AUTO: with nnz, the dense stencil and an occupancy-driven kernel (cost proportional to the
  *         occupied voxels) are both enqueued and the count selects ON THE DEVICE which of them works (sparse up
- *         to 3 % occupancy for kx*ky <= 64 taps per slice, 4 % above); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
+ *         to 3 % occupancy for kx*ky <= 64 taps per slice, 4 % above, and only for grids that are not clustered:
+ *         sn_select_fwd_path_state); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
  *         (measurement, tests).  Same pred either way up to float32 summation order.
  *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
  *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
@@ -163,6 +164,10 @@ int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, int mode, con
  * choice only affects speed).  which: 0 = forward, 1 = tap gradient.  Returns SN_PATH_DENSE / SN_PATH_SPARSE. */
 int sn_select_path(int which, int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
 int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
+/* The forward's rule with the clustering statistic of the state buffer (state[2] = mask words with >= 8 of 32 voxels
+ * occupied): a sparse but CLUSTERED grid (a locally dense layer, e.g. the ground of a LiDAR scan) goes to the dense
+ * stencil, because the occupancy-driven kernel's cost per tile follows the tile's own occupancy. */
+int sn_select_fwd_path_state(int64_t nnz, int64_t dense_words, int B, int Z, int X, int Y, int kz, int kx, int ky);
 
 /* The two passes of sn_scenenet_bwd, callable on their own (measurement, fused criterions that
  * produce G0 themselves):  G0 [n] float32 = dpred * (1 - pred^2) * [pred > 0] evaluated in float64 and
@@ -224,8 +229,9 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
  * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
  * nothing is copied) and the grid STATE buffer `nnz` the forward / backward take:
  *   [0] uint64 number of non-zero voxels, [1] uint64 ticket counter the tap-gradient kernels use to let their last
- *   CTA sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward), then from
- *   byte 16 one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel index i; ABI v3): the
+ *   CTA sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward), [2] uint64 number
+ *   of 32-voxel mask words with >= 8 voxels occupied (how clustered the grid is), [3] reserved, then from
+ *   byte 32 one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel index i; ABI v3): the
  *   occupancy-driven forward lists the non-zero voxels of a halo row from these words instead of scanning floats.
  * nnz: DEVICE buffer of sn_grid_state_bytes(n) bytes, 16-byte aligned; counters zeroed and bits written by the call.
  * x and x32 16-byte aligned. */

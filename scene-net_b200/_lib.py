@@ -58,6 +58,7 @@ SIGNATURES = {
     "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_select_path": (_i, [_i, _i64, _i, _i, _i, _i, _i, _i, _i]),
     "sn_select_fwd_path": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i]),
+    "sn_select_fwd_path_state": (_i, [_i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_g0": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_scenenet_tapgrad_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_tapgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),

@@ -37,30 +37,45 @@ __global__ void __launch_bounds__(256) cast_u8_f32_kernel(const unsigned char* _
 // the non-zero voxels of a halo row with one 64-bit load instead of scanning the floats).  Integer atomics only: the
 // count is exact and order-independent.
 // (one atomic per CTA: thousands of same-address atomics at the end of the kernel were a visible serial tail)
-__device__ __forceinline__ void add_count(unsigned cnt, unsigned long long* nnz) {
-    __shared__ unsigned s_cnt[8];
+// cnt -> nnz[0] (non-zero voxels), dense -> nnz[2] (mask words with >= kDenseWordBits bits set: how clustered the grid is)
+__device__ __forceinline__ void add_count(unsigned cnt, unsigned dense, unsigned long long* nnz) {
+    __shared__ unsigned s_cnt[8], s_dns[8];
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    dense = __reduce_add_sync(0xffffffffu, dense);
+    if ((threadIdx.x & 31) == 0) {
+        s_cnt[threadIdx.x >> 5] = cnt;
+        s_dns[threadIdx.x >> 5] = dense;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = 0;
+        unsigned t = 0, d = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += s_cnt[i];
+        for (int i = 0; i < 8; ++i) {
+            t += s_cnt[i];
+            d += s_dns[i];
+        }
         if (t) atomicAdd(nnz, (unsigned long long)t);
+        if (d) atomicAdd(nnz + 2, (unsigned long long)d);
     }
 }
 
 // A lane holds NB occupancy bits of NB consecutive voxels (lane l of the warp: voxels [(wb + l) * NB, +NB)); the
 // 32 / NB lanes of a group assemble one 32-bit mask word by a butterfly OR and the group leader stores it.  Call with
 // the whole warp converged; wb = chunk index of lane 0 (a multiple of 32).
+// Returns 1 on the lane that stored a word with at least kDenseWordBits of its 32 voxels occupied.
+constexpr int kDenseWordBits = 8;
 template <int NB>
-__device__ __forceinline__ void store_mask_words(unsigned bits, long long wb, unsigned* __restrict__ mask, long long nw) {
+__device__ __forceinline__ unsigned store_mask_words(unsigned bits, long long wb, unsigned* __restrict__ mask, long long nw) {
     constexpr int GL = 32 / NB;  // lanes per word
     const int lane = threadIdx.x & 31;
     unsigned v = bits << (NB * (lane % GL));
 #pragma unroll
     for (int o = 1; o < GL; o <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane % GL == 0 && (wb + lane) / GL < nw) mask[(wb + lane) / GL] = v;  // nw = ceil(n / 32) words hold live bits
+    if (lane % GL == 0 && (wb + lane) / GL < nw) {  // nw = ceil(n / 32) words hold live bits
+        mask[(wb + lane) / GL] = v;
+        return __popc(v) >= kDenseWordBits ? 1u : 0u;
+    }
+    return 0u;
 }
 
 __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __res
     const long long nw = (n + 31) >> 5;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0;
+    unsigned cnt = 0, dns = 0;
     long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane);
     for (; wb + 3 * stride + 32 <= n2; wb += 4 * stride) {  // all four steps are full for every lane of the warp
         double2 v[4];
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __res
             reinterpret_cast<float2*>(out)[wb + u * stride + lane] = o;
             const unsigned b = (o.x != 0.f ? 1u : 0u) | (o.y != 0.f ? 2u : 0u);
             cnt += __popc(b);
-            store_mask_words<2>(b, wb + u * stride, mask, nw);
+            dns += store_mask_words<2>(b, wb + u * stride, mask, nw);
         }
     }
     for (; wb < np; wb += stride) {  // remaining steps, element-wise bounds
@@ -100,9 +115,9 @@ __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __res
         }
         const unsigned b = (o.x != 0.f ? 1u : 0u) | (o.y != 0.f ? 2u : 0u);
         cnt += __popc(b);
-        store_mask_words<2>(b, wb, mask, nw);
+        dns += store_mask_words<2>(b, wb, mask, nw);
     }
-    add_count(cnt, nnz);
+    add_count(cnt, dns, nnz);
 }
 
 __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n,
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __
     const long long nc = (n + 15) >> 4;  // 16-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0;
+    unsigned cnt = 0, dns = 0;
     for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
         const long long i = wb + lane;
         unsigned bits = 0;
@@ -132,9 +147,9 @@ __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __
             }
         }
         cnt += __popc(bits);
-        store_mask_words<16>(bits, wb, mask, (n + 31) >> 5);
+        dns += store_mask_words<16>(bits, wb, mask, (n + 31) >> 5);
     }
-    add_count(cnt, nnz);
+    add_count(cnt, dns, nnz);
 }
 
 __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict__ in, long long n, unsigned long long* nnz,
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict_
     const long long nq = (n + 3) >> 2;  // 4-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0;
+    unsigned cnt = 0, dns = 0;
     for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nq; wb += stride) {
         const long long i = wb + lane;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -155,9 +170,9 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict_
         }
         const unsigned bits = (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
         cnt += __popc(bits);
-        store_mask_words<4>(bits, wb, mask, (n + 31) >> 5);
+        dns += store_mask_words<4>(bits, wb, mask, (n + 31) >> 5);
     }
-    add_count(cnt, nnz);
+    add_count(cnt, dns, nnz);
 }
 
 template <typename T>
@@ -216,8 +231,9 @@ extern "C" int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n,
 
 extern "C" int64_t sn_grid_state_bytes(int64_t n) {
     if (n < 0) return SN_ERR_BAD_ARG;
-    // count + ticket, one mask bit per voxel, 4 padding words (the forward reads word pairs), rounded to 16 bytes
-    return (16 + 4 * ((n + 31) / 32 + 4) + 15) & ~(int64_t)15;
+    // four counters (count, ticket, dense words, reserved), one mask bit per voxel, 4 padding words (the forward reads
+    // word pairs), rounded to 16 bytes
+    return (32 + 4 * ((n + 31) / 32 + 4) + 15) & ~(int64_t)15;
 }
 
 extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream) {
@@ -227,10 +243,10 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     if (dtype == SN_F32 && x32 && (const void*)x32 != x) return SN_ERR_BAD_ARG;  // float32 grids are used in place
     if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 15)) return SN_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(nnz, 0, 2 * sizeof(unsigned long long), s);  // [0] count, [1] ticket of the tap-gradient tail
+    cudaError_t e = cudaMemsetAsync(nnz, 0, 4 * sizeof(unsigned long long), s);  // [0] count, [1] ticket of the tap-gradient tail, [2] dense words
     if (e != cudaSuccess) return sn::cuda_rc(e);
     if (n == 0) return SN_OK;
-    unsigned* mask = reinterpret_cast<unsigned*>(nnz + 2);  // occupancy bits follow the two counters (sn_grid_state_bytes)
+    unsigned* mask = reinterpret_cast<unsigned*>(nnz + 4);  // occupancy bits follow the four counters (sn_grid_state_bytes)
     if (dtype == SN_F64)
         sn::prepare_f64_kernel<<<sn::grid_for(n / 2 + 1, 256 * 4), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
     else if (dtype == SN_U8)

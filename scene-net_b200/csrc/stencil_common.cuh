@@ -33,6 +33,15 @@ struct Geo {
     static constexpr int WN = round4(OFF + KY + 3);  // window floats a thread reads per input row
 };
 
+// Device-side selection of the forward kernel from sn_grid_prepare's state buffer: the occupancy-driven kernel works iff
+// the grid is sparse (st[0] = non-zero voxels) AND not clustered (st[2] = mask words with >= 8 of 32 voxels occupied).
+// Its cost per tile grows with the tile's own occupancy and tiles are assigned statically, so ONE locally dense tile
+// (the ground layer of a LiDAR scan) makes it slower than the dense stencil even when the grid as a whole is almost
+// empty: KITTI-shaped scans at 2.8 % overall occupancy with one layer at 35 % ran 294 us against 87 us dense.
+__device__ __forceinline__ bool fwd_sparse_selected(const unsigned long long* st, unsigned long long nnz_max, unsigned long long dw_max) {
+    return st[0] <= nnz_max && st[2] <= dw_max;
+}
+
 struct FwdParams {
     const float* x;
     const float* Kstar;
@@ -49,6 +58,7 @@ struct FwdParams {
     // at once when nnz != NULL and *nnz <= nnz_max
     const unsigned long long* nnz;
     unsigned long long nnz_max;
+    unsigned long long dw_max;  // clustering bound on st[2] (fwd_sparse_selected)
 };
 
 struct BwdParams {

@@ -23,8 +23,8 @@ int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // st
 // stencil_fwd_sparse.cu
 bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
-                      unsigned long long nnz_max, const unsigned* occ_mask, int B, int Z, int X, int Y, int kz, int kx, int ky,
-                      cudaStream_t stream);
+                      unsigned long long nnz_max, unsigned long long dw_max, const unsigned* occ_mask, int B, int Z, int X, int Y,
+                      int kz, int kx, int ky, cudaStream_t stream);
 }  // namespace sn
 
 // occupancy (percent of the voxels) up to which the occupancy-driven forward is selected: measured break-even on B200
@@ -35,6 +35,16 @@ static unsigned long long fwd_sparse_nnz_max(long long nvox, int kx, int ky) {
     static const double forced = getenv("SN_SPARSE_FWD_PCT") ? atof(getenv("SN_SPARSE_FWD_PCT")) : -1.0;
     const double pct = forced >= 0.0 ? forced : (kx * ky <= 64 ? 3.0 : 4.0);
     return (unsigned long long)((double)nvox * pct / 100.0);
+}
+
+// Clustering bound: mask words with >= 8 of their 32 voxels occupied that a grid may hold and still go to the
+// occupancy-driven kernel.  A uniformly sparse grid has none (Bernoulli 3 %: 7e-6 of the words); a grid with a locally dense
+// layer has thousands.  16 words or 1/4096 of all words, whichever is larger.
+static unsigned long long fwd_dense_words_max(long long nvox) {
+    static const long long forced = getenv("SN_SPARSE_FWD_DW") ? atoll(getenv("SN_SPARSE_FWD_DW")) : -1;
+    if (forced >= 0) return (unsigned long long)forced;
+    const long long nw = (nvox + 31) / 32;
+    return (unsigned long long)(nw / 4096 > 16 ? nw / 4096 : 16);
 }
 
 static int dense_fwd(const sn::FwdParams& p, int ky, cudaStream_t s) {
@@ -62,36 +72,44 @@ extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, in
     if (mode != SN_PATH_AUTO && mode != SN_PATH_DENSE && mode != SN_PATH_SPARSE) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
     if (nnz && ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
-    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, nullptr, 0};
+    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, nullptr, 0, 0};
     cudaStream_t s = (cudaStream_t)stream;
     const bool sparse_ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
     // sn_grid_prepare's state buffer: count, ticket, then one occupancy bit per voxel (sn_grid_state_bytes)
-    const unsigned* occ = nnz ? reinterpret_cast<const unsigned*>(nnz + 2) : nullptr;
+    const unsigned* occ = nnz ? reinterpret_cast<const unsigned*>(nnz + 4) : nullptr;
+    const unsigned long long dw_max = fwd_dense_words_max((long long)B * Z * X * Y);
     const unsigned long long nnz_max = fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky);
     if (mode == SN_PATH_SPARSE) {
         if (!sparse_ok) return SN_ERR_UNSUPPORTED;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
     }
     if (mode == SN_PATH_AUTO && sparse_ok && nnz) {
         // both kernels are enqueued; the non-zero count decides on the device which one works
-        p.nnz = nnz; p.nnz_max = nnz_max;
+        p.nnz = nnz; p.nnz_max = nnz_max; p.dw_max = dw_max;
         int rc = dense_fwd(p, ky, s);
         if (rc == SN_ERR_UNSUPPORTED)  // no dense instantiation for this width: the occupancy-driven kernel always runs
-            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
+            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
         if (rc) return rc;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, occ, B, Z, X, Y, kz, kx, ky, s);
+        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, dw_max, occ, B, Z, X, Y, kz, kx, ky, s);
     }
     int rc = dense_fwd(p, ky, s);
     if (rc == SN_ERR_UNSUPPORTED) {
-        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, occ, B, Z, X, Y, kz, kx, ky, s);
+        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
         rc = sn::stencil_fwd_generic(p, ky, s);
     }
     return rc;
 }
 
-extern "C" int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky) {
+extern "C" int sn_select_fwd_path_state(int64_t nnz, int64_t dense_words, int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1 || nnz < 0 || dense_words < 0) return SN_ERR_BAD_ARG;
     const bool ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
     const bool fast = ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15;
     if (ok && !fast) return SN_PATH_SPARSE;
-    return (ok && (unsigned long long)nnz <= fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky)) ? SN_PATH_SPARSE : SN_PATH_DENSE;
+    const long long nvox = (long long)B * Z * X * Y;
+    return (ok && (unsigned long long)nnz <= fwd_sparse_nnz_max(nvox, kx, ky) && (unsigned long long)dense_words <= fwd_dense_words_max(nvox))
+               ? SN_PATH_SPARSE : SN_PATH_DENSE;
+}
+
+extern "C" int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    return sn_select_fwd_path_state(nnz, 0, B, Z, X, Y, kz, kx, ky);
 }

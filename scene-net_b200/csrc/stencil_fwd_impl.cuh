@@ -95,7 +95,7 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
 template <int KY, int TYT, int REM>
 __global__ void __launch_bounds__(kStencilThreads, 4)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
-    if (p.nnz && *p.nnz <= p.nnz_max) return;  // sparse input: fwd_sparse_kernel does the work
+    if (p.nnz && fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // sparse input: the occupancy-driven kernel does the work
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);

@@ -34,7 +34,8 @@ struct FsParams {
     const float* Kstar;
     void* pred;
     const unsigned long long* nnz;  // device; NULL = always run
-    unsigned long long nnz_max;     // run iff *nnz <= nnz_max
+    unsigned long long nnz_max;     // run iff *nnz <= nnz_max ...
+    unsigned long long dw_max;      // ... and nnz[2] <= dw_max (not clustered)
     int B, Z, X, Y, kz, kx, ky;
     int out_f64, tanh64;
     int IX, IY;                 // output tile (z extent kRZ)
@@ -64,7 +65,7 @@ struct FsScan {
 template <int NI2>
 __global__ void __launch_bounds__(kFsThreads, 4)
 fwd_sparse_kernel(const FsParams p) {
-    if (p.nnz && *p.nnz > p.nnz_max) return;  // dense input: stencil_fwd_kernel does the work
+    if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // dense or clustered input: stencil_fwd_kernel does the work
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_floats = p.RP * p.AS;
     const int P = p.kx * p.ky, T = p.kz * P;
@@ -292,7 +293,7 @@ __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) 
 template <int NI2, bool OUT64>
 __global__ void __launch_bounds__(kFsThreads, NI2 <= 2 ? 4 : 3)
 fwd_occ_kernel(const FsParams p) {
-    if (p.nnz && *p.nnz > p.nnz_max) return;  // dense input: stencil_fwd_kernel does the work
+    if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // dense or clustered input: stencil_fwd_kernel does the work
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_floats = p.RP * p.AS;
     const int P = p.kx * p.ky, T = p.kz * P;
@@ -583,13 +584,13 @@ static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
 }
 
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
-                      unsigned long long nnz_max, const unsigned* occ_mask, int B, int Z, int X, int Y, int kz, int kx, int ky,
-                      cudaStream_t stream) {
+                      unsigned long long nnz_max, unsigned long long dw_max, const unsigned* occ_mask, int B, int Z, int X, int Y,
+                      int kz, int kx, int ky, cudaStream_t stream) {
     FsParams p{};
     size_t smem;
     int ni2;
     if (!plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2)) return SN_ERR_UNSUPPORTED;
-    p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = nnz; p.nnz_max = nnz_max;
+    p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = nnz; p.nnz_max = nnz_max; p.dw_max = dw_max;
     p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
     {
         static const bool no_mask = getenv("SN_FWD_NO_MASK") != nullptr;  // measurement: force the scanning kernel

@@ -324,12 +324,14 @@ def scenenet_bwd(x32: torch.Tensor, pred: torch.Tensor, dpred: torch.Tensor, ker
 
 
 def select_paths(x: torch.Tensor, kernel_size) -> tuple:
-    """(forward mode, backward mode) the device-side selection would pick for grids like `x` — reads the non-zero count
-    on the host (one synchronisation; meant for capture time, see graphs.GraphedStep)."""
+    """(forward mode, backward mode) the device-side selection would pick for grids like `x` — reads the grid state
+    (non-zero count, clustering statistic) on the host (one synchronisation; meant for capture time, see
+    graphs.GraphedStep)."""
     B, Z, X, Y = _grid_dims(x)
     kz, kx, ky = (int(v) for v in kernel_size)
-    n = int(torch.count_nonzero(x))
-    return (int(lib.sn_select_path(0, n, B, Z, X, Y, kz, kx, ky)), int(lib.sn_select_path(1, n, B, Z, X, Y, kz, kx, ky)))
+    _, st = prepare(x.detach())
+    n, dw = (int(v) for v in st[:3:2].tolist())
+    return (int(lib.sn_select_fwd_path_state(n, dw, B, Z, X, Y, kz, kx, ky)), int(lib.sn_select_path(1, n, B, Z, X, Y, kz, kx, ky)))
 
 
 def g0(pred: torch.Tensor, dpred: torch.Tensor) -> torch.Tensor:

@@ -16,7 +16,7 @@ def _ops():
 
 
 def _bits(state, n):
-    w = state[2:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
+    w = state[4:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
     return np.unpackbits(w.view("uint8"), bitorder="little")[:n]
 
 
@@ -42,6 +42,8 @@ def test_prepare_state_bits(shape, dt):
         ref = (x != 0).flatten().cpu().numpy().astype("uint8")
         assert int(st[0]) == int(ref.sum()) and int(st[1]) == 0
         assert np.array_equal(_bits(st, n), ref)
+        words = np.add.reduceat(np.pad(ref, (0, (-n) % 32)).astype(np.int64), np.arange(0, n + (-n) % 32, 32))
+        assert int(st[2]) == int((words >= 8).sum())  # clustering statistic: 32-voxel words with >= 8 voxels occupied
         assert torch.equal(x32, x.float())
 
 
@@ -77,3 +79,28 @@ def test_float64_tanh_of_the_occupancy_forward():
     x32, st = ops.prepare(x)
     pred = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=2)
     assert float((pred - torch.tanh(x.double())).abs().max()) < 1e-11
+
+
+def test_clustered_grids_go_to_the_dense_stencil():
+    """a grid that is sparse overall (2 %) but has one dense layer: the device-side selection must pick the dense stencil
+    (the occupancy-driven kernel's cost follows the densest tile), a uniformly sparse grid of the same occupancy the
+    occupancy-driven kernel; results agree either way"""
+    ops = _ops()
+    from scenenet_b200._lib import lib
+    g = torch.Generator(device=DEV).manual_seed(9)
+    shape, ks = (4, 1, 64, 64, 64), (9, 5, 5)
+    uniform = (torch.rand(shape, generator=g, device=DEV) < 0.02).double()
+    layered = torch.zeros(shape, dtype=torch.float64, device=DEV)
+    layered[:, :, 30:32] = (torch.rand((4, 1, 2, 64, 64), generator=g, device=DEV) < 0.6).double()  # 1.9 % overall
+    K = torch.randn(ks, generator=g, device=DEV) * 0.2
+    for x, want in ((uniform, 2), (layered, 1)):
+        x32, st = ops.prepare(x)
+        n, dw = int(st[0]), int(st[2])
+        assert n <= 0.03 * x.numel()
+        assert lib.sn_select_fwd_path_state(n, dw, 4, 64, 64, 64, *ks) == want
+        assert ops.select_paths(x, ks)[0] == want
+        auto = ops.scenenet_fwd(x32, K, torch.float64, nnz=st)
+        forced = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=want)
+        assert torch.equal(auto, forced)
+        other = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=3 - want)
+        assert float((auto - other).abs().max()) < 5e-6
