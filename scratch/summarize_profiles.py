@@ -32,8 +32,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 REPS = {"r1b": [("gpurun_out/prof_r1_step.ncu-rep", "r1b_ncu_step_kernels.csv"), ("gpurun_out/prof_fsparse_r1.ncu-rep", "r1b_ncu_fwd_sparse.csv"),
                 ("gpurun_out/prof_bin_r1.ncu-rep", "r1b_ncu_vox_bin.csv")],
         # third part of the round: mask-driven occupancy forward (1.6 % and empty grids), scanning kernel before it, prepare with the bit mask
-        "r1c": [("gpurun_out/prof_fo_r1g.ncu-rep", "r1c_ncu_fwd_occ.csv"), ("gpurun_out/prof_fo0_r1d.ncu-rep", "r1c_ncu_fwd_occ_empty_grids.csv"),
-                ("gpurun_out/prof_fs_r1c.ncu-rep", "r1c_ncu_fwd_scan_before.csv"), ("gpurun_out/prof_prep_r1d.ncu-rep", "r1c_ncu_prepare.csv")]}
+        "r1c": [("gpurun_out/prof_fo_r1h.ncu-rep", "r1c_ncu_fwd_occ.csv"), ("gpurun_out/prof_fo0_r1d.ncu-rep", "r1c_ncu_fwd_occ_empty_grids.csv"),
+                ("gpurun_out/prof_fs_r1c.ncu-rep", "r1c_ncu_fwd_scan_before.csv"), ("gpurun_out/prof_prep_r1h.ncu-rep", "r1c_ncu_prepare.csv")]}
 for rep, name in REPS.get(tag, []):
     if not os.path.exists(rep):
         continue
