@@ -218,9 +218,12 @@ int sn_criterion_bwd(const void* pred, const void* y, int dtype, int64_t n, cons
  * 0 = relu(-v) regulariser term, 2 = free convex coefficient (relu(-v), and part of the coefficient sum),
  * 1 = the frozen last coefficient (contributes relu(-(1 - sum(all coefficients) + itself))).
  * out (DEVICE, 2 + n floats): [0] = weight * cvx_loss, [1] = weight * positive_regularizer,
- * [2 + i] = d(out[0] + out[1]) / d param_i. */
+ * [2 + i] = d(out[0] + out[1]) / d param_i.
+ * loss_accum (nullable): DEVICE double, e.g. the loss written by sn_criterion_fwd earlier on the same stream; the two
+ * penalties are added to it in the reference's order, (loss + out[0]) + out[1] (geneo_loss.py:161), so that the
+ * whole GENEO_Tversky_Loss value is produced by the library's three launches. */
 int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_host, int n, float weight,
-                     float* out, void* stream);
+                     float* out, double* loss_accum, void* stream);
 
 /* ======================================================================================
  * elementwise helpers

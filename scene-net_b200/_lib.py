@@ -67,7 +67,7 @@ SIGNATURES = {
     "sn_criterion_workspace_bytes": (_i64, [_i64]),
     "sn_criterion_fwd": (_i, [_vp, _vp, _i, _i64, _fp, _fp, _i, C.c_float, _d, _d, _d, _d, _i, _vp, _vp, _vp, _i64, _vp]),
     "sn_criterion_bwd": (_i, [_vp, _vp, _i, _i64, _fp, _fp, _i, _vp, _vp, _vp, _i, _vp]),
-    "sn_param_penalty": (_i, [_pp, C.POINTER(C.c_int32), _i, C.c_float, _vp, _vp]),
+    "sn_param_penalty": (_i, [_pp, C.POINTER(C.c_int32), _i, C.c_float, _vp, _vp, _vp]),
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),

@@ -1,9 +1,9 @@
 """GENEO losses — drop-in mirror of the reference's core/criterions/geneo_loss.py (GENEO_Loss :24-91,
 GENEO_Tversky_Loss :145-168): same constructors and `forward(y_pred, y_gt, cvx_coeffs, geneo_params)`.
 
-`forward` is four launches (fused reduction over (pred, y), one-warp finalisation, one penalty kernel over
-the live parameters, two scalar adds) instead of ~80 ATen ops; the backward is one elementwise kernel for
-dL/dpred plus one scaled copy of the penalty gradients.  The penalty terms act on the live nn.Parameters
+`forward` is ONE autograd node of three launches (fused reduction over (pred, y), finalisation, one penalty kernel
+over the live parameters that also adds its two terms to the loss scalar) instead of ~80 ATen ops; the backward is one
+elementwise kernel for dL/dpred plus one scaled copy of the penalty gradients.  The penalty terms act on the live nn.Parameters
 handed in, exactly like the reference's (`cvx_loss`, `positive_regularizer`).
 """
 from __future__ import annotations
@@ -47,8 +47,8 @@ class _PenaltyFunction(torch.autograd.Function):
         return (None, None, *grads)
 
 
-def _penalties(cvx_coeffs, geneo_params, weight):
-    """-> (cvx_penalty, positive_penalty) tensors; either mapping may be empty."""
+def _collect(cvx_coeffs, geneo_params):
+    """(parameter list, role list) in the reference's summation order (geneo_loss.py:36-71)"""
     params, roles = [], []
     if len(cvx_coeffs) > 0:
         # geneo_loss.py:48: the frozen coefficient is the one computed from the others
@@ -59,6 +59,39 @@ def _penalties(cvx_coeffs, geneo_params, weight):
     for g in geneo_params.values():
         params.append(g)
         roles.append(0)
+    return params, roles
+
+
+class _FusedGeneoCriterion(torch.autograd.Function):
+    """The whole GENEO loss as ONE autograd node: [weighted MSE] + [focal Tversky] + cvx penalty + positive regulariser.
+    Forward = three launches (reduction over (pred, y), finalisation, penalty kernel that also adds its two terms to
+    the loss scalar); backward = the closed-form dL/dpred kernel + one scaled copy of the penalty gradients.  (As
+    separate nodes joined by torch adds the step carried eight more elementwise launches of autograd glue.)"""
+
+    @staticmethod
+    def forward(ctx, pred, y, spec, roles, weight, *params):
+        loss, coef, p, t = ops.criterion_fwd(pred.detach(), y.detach(), spec)
+        out = ops.param_penalty([q.detach() for q in params], roles, weight, loss_accum=loss)
+        ctx.spec, ctx.shape = spec, pred.shape
+        ctx.save_for_backward(p, t, coef, out)
+        return loss if pred.dtype == torch.float64 else loss.to(pred.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t, coef, out = ctx.saved_tensors
+        d = None
+        if ctx.needs_input_grad[0]:
+            d = ops.criterion_bwd(p, t, coef, ctx.spec, grad_out=g)
+            if d.shape != ctx.shape:  # pred was broadcast against y
+                d = d.sum_to_size(ctx.shape)
+        dp = out[2:] * g.to(torch.float32)
+        grads = [dp[i] if ctx.needs_input_grad[5 + i] else None for i in range(dp.numel())]
+        return (d, None, None, None, None, *grads)
+
+
+def _penalties(cvx_coeffs, geneo_params, weight):
+    """-> (cvx_penalty, positive_penalty) tensors; either mapping may be empty."""
+    params, roles = _collect(cvx_coeffs, geneo_params)
     return _PenaltyFunction.apply(roles, float(weight), *params)
 
 
@@ -85,10 +118,15 @@ class GENEO_Loss(WeightedMSE):
         cvx, pos = _penalties(cvx_coeffs, geneo_params, self.cvx_w)
         return (cvx if len(cvx_coeffs) else 0), (pos if len(geneo_params) else 0)
 
+    def _fused(self, y_pred, y_gt, spec, cvx_coeffs, geneo_params):
+        params, roles = _collect(cvx_coeffs, geneo_params)
+        if not params:  # no parameters handed in: the data terms alone
+            return _FusedCriterion.apply(y_pred, y_gt, spec)
+        return _FusedGeneoCriterion.apply(y_pred, y_gt, spec, roles, float(self.cvx_w), *params)
+
     def forward(self, y_pred: torch.Tensor, y_gt: torch.Tensor, cvx_coeffs: torch.nn.ParameterDict, geneo_params: torch.nn.ParameterDict):
-        dense_criterion = super().forward(y_pred, y_gt)
-        cvx_penalty, non_positive_penalty = self._both_penalties(cvx_coeffs, geneo_params)
-        return dense_criterion + cvx_penalty + non_positive_penalty
+        # dense_criterion + cvx_penalty + non_positive_penalty (geneo_loss.py:73-91)
+        return self._fused(y_pred, y_gt, self._spec(1), cvx_coeffs, geneo_params)
 
     def __str__(self):
         return f"GENEO Loss with mse_weight={self.mse_weight} and alpha={self.weight_alpha} and epsilon={self.weight_epsilon}"
@@ -114,10 +152,8 @@ class GENEO_Tversky_Loss(GENEO_Loss):
                           focal_gamma=float(t.focal_gamma), tversky_smooth=float(t.tversky_smooth))
 
     def forward(self, y_pred: torch.Tensor, y_gt: torch.Tensor, cvx_coeffs: torch.nn.ParameterDict, geneo_params: torch.nn.ParameterDict):
-        # dense_criterion + tversky_crit in one reduction (geneo_loss.py:155-161)
-        dense_and_tversky = _FusedCriterion.apply(y_pred, y_gt, self.fused_spec())
-        cvx_penalty, non_positive_penalty = self._both_penalties(cvx_coeffs, geneo_params)
-        return dense_and_tversky + cvx_penalty + non_positive_penalty
+        # dense_criterion + tversky_crit + cvx_penalty + non_positive_penalty as one node (geneo_loss.py:155-161)
+        return self._fused(y_pred, y_gt, self.fused_spec(), cvx_coeffs, geneo_params)
 
     def training_loss(self, model, x: torch.Tensor, y_gt: torch.Tensor):
         """(loss, pred) of `model` on (x, y_gt) — extension: the observer forward and this criterion as ONE autograd

@@ -233,7 +233,10 @@ struct PenaltyArgs {
     signed char role[SN_MAX_PARAM_PTRS];
     int n;
 };
-__global__ void __launch_bounds__(128) penalty_kernel(const __grid_constant__ PenaltyArgs a, float weight, float* __restrict__ out) {
+// loss_accum (nullable): the criterion's float64 loss scalar; both penalties are added to it here, in the reference's
+// order ((loss + cvx) + pos, float32 terms widened), so the host adds nothing afterwards
+__global__ void __launch_bounds__(128) penalty_kernel(const __grid_constant__ PenaltyArgs a, float weight, float* __restrict__ out,
+                                                      double* __restrict__ loss_accum) {
     __shared__ float s_v[SN_MAX_PARAM_PTRS];
     if (threadIdx.x < a.n) s_v[threadIdx.x] = *a.p[threadIdx.x];  // all parameter loads in flight at once
     __syncthreads();
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(128) penalty_kernel(const __grid_constant__ Pe
     }
     out[0] = weight * cvx;
     out[1] = weight * pos;
+    if (loss_accum) *loss_accum = (*loss_accum + (double)(weight * cvx)) + (double)(weight * pos);
 }
 
 static int crit_grid(long long n) {
@@ -350,7 +354,7 @@ extern "C" int sn_criterion_bwd(const void* pred, const void* y, int dtype, int6
 }
 
 extern "C" int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_host, int n, float weight,
-                                float* out, void* stream) {
+                                float* out, double* loss_accum, void* stream) {
     if (!param_ptrs_host || !role_host || !out || n < 0 || n > SN_MAX_PARAM_PTRS) return SN_ERR_BAD_ARG;
     sn::PenaltyArgs a;
     a.n = n;
@@ -364,7 +368,8 @@ extern "C" int sn_param_penalty(const float* const* param_ptrs_host, const int32
         }
     }
     if (n_last > 1) return SN_ERR_BAD_ARG;
-    sn::penalty_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(a, weight, out);
+    if ((uintptr_t)loss_accum & 7) return SN_ERR_ALIGN;
+    sn::penalty_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(a, weight, out, loss_accum);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

@@ -423,8 +423,12 @@ def criterion_bwd(pred: torch.Tensor, y: torch.Tensor, coef: torch.Tensor, spec:
     return out
 
 
-def param_penalty(params: Sequence[torch.Tensor], roles: Sequence[int], weight: float) -> torch.Tensor:
-    """-> float32 [2 + n]: weight * cvx_loss, weight * positive_regularizer, d(sum of both)/d param_i."""
+def param_penalty(params: Sequence[torch.Tensor], roles: Sequence[int], weight: float,
+                  loss_accum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """-> float32 [2 + n]: weight * cvx_loss, weight * positive_regularizer, d(sum of both)/d param_i.
+    loss_accum: float64 scalar device tensor the two penalties are ADDED to in place (the criterion's loss)."""
+    if loss_accum is not None and (loss_accum.dtype != torch.float64 or loss_accum.numel() != 1 or not loss_accum.is_cuda):
+        raise TypeError("loss_accum must be a float64 scalar on the device")
     n = len(params)
     if n > _lib.SN_MAX_PARAM_PTRS:
         raise ValueError(f"at most {_lib.SN_MAX_PARAM_PTRS} parameters")
@@ -432,7 +436,7 @@ def param_penalty(params: Sequence[torch.Tensor], roles: Sequence[int], weight: 
     out = torch.empty(2 + n, dtype=torch.float32, device=dev)
     with _on_device(dev):
         check(lib.sn_param_penalty(_ptr_array(params), (C.c_int32 * n)(*[int(r) for r in roles]), n, float(weight),
-                                   out.data_ptr(), _stream()), "sn_param_penalty")
+                                   out.data_ptr(), _ptr(loss_accum), _stream()), "sn_param_penalty")
     return out
 
 
