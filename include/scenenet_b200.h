@@ -146,7 +146,7 @@ int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, con
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
  *   G0 = dpred * (1 - pred^2) * [pred > 0];   W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t]
  *   x [B,1,Z,X,Y] float32, pred / dpred in pred_dtype / dpred_dtype, W [T] float64 out.
- *   nnz: DEVICE pointer to the two-word count buffer of x as written by sn_grid_prepare, or NULL.
+ *   nnz: DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count at [0], ticket at [1]), or NULL.
  *        Voxel grids of point clouds are ~98 % empty: when nnz is given, an occupancy-driven
  *        kernel (cost proportional to the occupied voxels) and the dense stencil are both enqueued and the
  *        count selects ON THE DEVICE which of them does the work (sparse up to 10 % occupancy; no host

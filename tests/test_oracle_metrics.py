@@ -49,3 +49,20 @@ def test_oracle_degenerate_and_accumulation():
     assert coll.compute() == mx.values_from_counts(tot)
     coll.reset()
     assert coll.state.sum() == 0
+
+
+def test_collection_value_formulas_on_cpu_tensors():
+    """the float32 formulas of the drop-in collection (scene-net_b200/utils/scripts_utils.py::_values) against the
+    oracle for random and degenerate count vectors — pure torch arithmetic on [tp, fp, tn, fn], no kernel involved"""
+    import torch
+    from scenenet_b200.utils.scripts_utils import _values, METRIC_NAMES
+    rng = np.random.default_rng(7)
+    cases = [rng.integers(0, 10 ** rng.integers(1, 8), 4) for _ in range(200)]
+    cases += [np.array(c) for c in ([0, 0, 0, 0], [0, 0, 100, 0], [5, 0, 0, 0], [0, 7, 0, 0], [0, 0, 0, 9], [1, 1, 1, 1])]
+    for c in cases:
+        got = _values(torch.tensor(c, dtype=torch.int64))
+        want = mx.values_from_counts(c)
+        assert list(got.keys()) == list(METRIC_NAMES)
+        for k in METRIC_NAMES:
+            assert got[k].dtype == torch.float32
+            assert abs(float(got[k]) - float(want[k])) <= 1.2e-7, (c, k, float(got[k]), float(want[k]))
