@@ -141,6 +141,13 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
 #define SN_PATH_SPARSE 2
 int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype, void* stream);
+/* Several observers on the SAME grids — SCENENetQuantile.forward (SCENE_Net.py:409-415: one SCENE_Net per quantile,
+ * predictions concatenated).  Kstars [n_observers][T] float32, preds [n_observers][B,1,Z,X,Y] out.
+ * The occupancy-driven kernel lists the non-zero voxels of a tile once and scatters them with every observer's taps
+ * (x is read once); the dense stencil runs once per observer.  Selection as in sn_scenenet_fwd.  n_observers <= 8. */
+#define SN_MAX_OBSERVERS 8
+int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, int n_observers,
+                          int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype, void* stream);
 
 /* Observer backward, data part — replaces aten::convolution_backward (weight gradient) and
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.

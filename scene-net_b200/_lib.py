@@ -54,6 +54,7 @@ SIGNATURES = {
     "sn_geneo_synth_bwd": (_i, [_descp, _pp, _vp, _vp, _vp]),
     "sn_scenenet_param_grads": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _vp]),
     "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd_multi": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_select_path": (_i, [_i, _i64, _i, _i, _i, _i, _i, _i, _i]),

@@ -377,10 +377,27 @@ class SCENENetQuantile(nn.Module):
         return [scnet.get_geneo_params() for scnet in self.scnets]
 
     def forward(self, x: torch.Tensor):
-        # SCENE_Net.py:409-415: every quantile's observer reads the same grids — the float32 copy and the non-zero
-        # count are produced once and shared (the observers then differ only in their 13 scalars)
+        # SCENE_Net.py:409-415: every quantile's observer reads the same grids — the float32 copy and the grid state are
+        # produced once and shared (the observers then differ only in their 13 scalars)
         prepared = ops.prepare(x.detach()) if x.is_cuda else None
-        return torch.cat([net(x, _prepared=prepared).to(torch.float32) for net in self.scnets], dim=1)
+        nets = list(self.scnets)
+        sizes = {tuple(net._spec_and_params()[0].kernel_size) for net in nets} if x.is_cuda else set()
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if x.is_cuda and not needs_grad and len(sizes) == 1 and 1 < len(nets) <= 8 and x.numel():
+            # inference: ONE forward for all quantiles (sn_scenenet_fwd_multi) — the occupancy-driven kernel lists the
+            # non-zero voxels of a tile once and scatters them with every observer's taps.  Same values as the
+            # per-observer path below (same kernels, same summation order).
+            x32, state = prepared
+            kstars = []
+            for net in nets:
+                spec, params = net._spec_and_params()
+                kstars.append(ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=True)[2])
+            out_dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+            modes = {tuple(net.path_modes) for net in nets}
+            mode = modes.pop()[0] if len(modes) == 1 else 0
+            preds = ops.scenenet_fwd_multi(x32, torch.stack(kstars), out_dtype, nnz=state, mode=mode)  # [Q,B,1,Z,X,Y]
+            return preds[:, :, 0].permute(1, 0, 2, 3, 4).to(torch.float32).contiguous()
+        return torch.cat([net(x, _prepared=prepared).to(torch.float32) for net in nets], dim=1)
 
 
 class SCENE_Net_Class(nn.Module):

@@ -24,7 +24,7 @@ int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // st
 bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
                       unsigned long long nnz_max, unsigned long long dw_max, const unsigned* occ_mask, int B, int Z, int X, int Y,
-                      int kz, int kx, int ky, cudaStream_t stream);
+                      int kz, int kx, int ky, int nq, cudaStream_t stream);
 }  // namespace sn
 
 // occupancy (percent of the voxels) up to which the occupancy-driven forward is selected: measured break-even on B200
@@ -63,41 +63,74 @@ static int dense_fwd(const sn::FwdParams& p, int ky, cudaStream_t s) {
     return rc;
 }
 
-extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
-                               int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype,
-                               void* stream) {
+// nq observers on the same grids: Kstar [nq][T], pred [nq][B,1,Z,X,Y].  The dense stencil runs once per observer; the
+// mask-driven occupancy kernel lists the non-zero voxels of a tile once for all of them.
+static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, int nq, int B, int Z, int X, int Y,
+                    int kz, int kx, int ky, void* pred, int pred_dtype, void* stream) {
     if (!x || !Kstar || !pred) return SN_ERR_BAD_ARG;
-    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1) return SN_ERR_BAD_ARG;
+    if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1 || nq < 1 || nq > SN_MAX_OBSERVERS) return SN_ERR_BAD_ARG;
     if (pred_dtype != SN_F32 && pred_dtype != SN_F64) return SN_ERR_BAD_ARG;
     if (mode != SN_PATH_AUTO && mode != SN_PATH_DENSE && mode != SN_PATH_SPARSE) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
     if (nnz && ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
-    sn::FwdParams p{x, Kstar, pred, B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, nullptr, 0, 0};
+    const long long T = (long long)kz * kx * ky, nvox = (long long)B * Z * X * Y;
+    const size_t esz = pred_dtype == SN_F64 ? 8 : 4;
     cudaStream_t s = (cudaStream_t)stream;
     const bool sparse_ok = sn::fwd_sparse_supported(B, Z, X, Y, kz, kx, ky);
-    // sn_grid_prepare's state buffer: count, ticket, then one occupancy bit per voxel (sn_grid_state_bytes)
+    // sn_grid_prepare's state buffer: count, ticket, clustering statistic, then one occupancy bit per voxel (sn_grid_state_bytes)
     const unsigned* occ = nnz ? reinterpret_cast<const unsigned*>(nnz + 4) : nullptr;
-    const unsigned long long dw_max = fwd_dense_words_max((long long)B * Z * X * Y);
-    const unsigned long long nnz_max = fwd_sparse_nnz_max((long long)B * Z * X * Y, kx, ky);
+    const unsigned long long dw_max = fwd_dense_words_max(nvox);
+    const unsigned long long nnz_max = fwd_sparse_nnz_max(nvox, kx, ky);
+    auto pred_q = [&](int q) { return (void*)((char*)pred + (size_t)q * (size_t)nvox * esz); };
+    auto dense_all = [&](const unsigned long long* gate, bool allow_generic) -> int {
+        for (int q = 0; q < nq; ++q) {
+            sn::FwdParams p{x, Kstar + q * T, pred_q(q), B, Z, X, Y, kz, kx, pred_dtype == SN_F64, 0, 0, sn::pad_left(kz), 0, gate, nnz_max, dw_max};
+            int rc = dense_fwd(p, ky, s);
+            if (rc == SN_ERR_UNSUPPORTED && allow_generic) rc = sn::stencil_fwd_generic(p, ky, s);
+            if (rc) return rc;
+        }
+        return SN_OK;
+    };
+    auto sparse_all = [&](const unsigned long long* gate) -> int {
+        int rc = sn::fwd_sparse_launch(x, Kstar, pred, pred_dtype == SN_F64, gate, nnz_max, dw_max, occ, B, Z, X, Y, kz, kx, ky, nq, s);
+        if (rc != SN_ERR_UNSUPPORTED || nq == 1) return rc;
+        for (int q = 0; q < nq; ++q) {  // no shared lists (no state buffer / shape outside the mask-driven kernel): one launch each
+            rc = sn::fwd_sparse_launch(x, Kstar + q * T, pred_q(q), pred_dtype == SN_F64, gate, nnz_max, dw_max, occ, B, Z, X, Y, kz, kx,
+                                       ky, 1, s);
+            if (rc) return rc;
+        }
+        return SN_OK;
+    };
     if (mode == SN_PATH_SPARSE) {
         if (!sparse_ok) return SN_ERR_UNSUPPORTED;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
+        return sparse_all(nullptr);
     }
     if (mode == SN_PATH_AUTO && sparse_ok && nnz) {
-        // both kernels are enqueued; the non-zero count decides on the device which one works
-        p.nnz = nnz; p.nnz_max = nnz_max; p.dw_max = dw_max;
-        int rc = dense_fwd(p, ky, s);
+        // both kernels are enqueued; the grid state decides on the device which one works
+        int rc = dense_all(nnz, false);
         if (rc == SN_ERR_UNSUPPORTED)  // no dense instantiation for this width: the occupancy-driven kernel always runs
-            return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
+            return sparse_all(nullptr);
         if (rc) return rc;
-        return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nnz, nnz_max, dw_max, occ, B, Z, X, Y, kz, kx, ky, s);
+        return sparse_all(nnz);
     }
-    int rc = dense_fwd(p, ky, s);
+    int rc = dense_all(nullptr, false);
     if (rc == SN_ERR_UNSUPPORTED) {
-        if (sparse_ok && mode == SN_PATH_AUTO) return sn::fwd_sparse_launch(x, Kstar, pred, p.out_f64, nullptr, 0, 0, occ, B, Z, X, Y, kz, kx, ky, s);
-        rc = sn::stencil_fwd_generic(p, ky, s);
+        if (sparse_ok && mode == SN_PATH_AUTO) return sparse_all(nullptr);
+        rc = dense_all(nullptr, true);
     }
     return rc;
+}
+
+extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
+                               int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype,
+                               void* stream) {
+    return fwd_impl(x, nnz, mode, Kstar, 1, B, Z, X, Y, kz, kx, ky, pred, pred_dtype, stream);
+}
+
+extern "C" int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, int n_observers,
+                                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype,
+                                     void* stream) {
+    return fwd_impl(x, nnz, mode, Kstars, n_observers, B, Z, X, Y, kz, kx, ky, preds, pred_dtype, stream);
 }
 
 extern "C" int sn_select_fwd_path_state(int64_t nnz, int64_t dense_words, int B, int Z, int X, int Y, int kz, int kx, int ky) {

@@ -46,6 +46,10 @@ struct FsParams {
     unsigned ws_magic;          // ceil(2^24 / WS): f / WS == (f * ws_magic) >> 24 for f < 2^13
     const unsigned* mask;       // occupancy bits of x by flat voxel index (sn_grid_prepare), nw words; fwd_occ_kernel only
     int nw;
+    // several observers on the same grids (SCENENetQuantile): Kstar holds nq tap sets [nq][T], pred nq
+    // outputs pred_qstride elements apart; the non-zero voxels of a tile are listed ONCE for all of them (fwd_occ_kernel)
+    int nq;
+    long long pred_qstride;
 };
 
 struct FsEntry {
@@ -290,9 +294,10 @@ __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) 
         : "memory");
 }
 
-template <int NI2, bool OUT64>
+template <int NI2, bool OUT64, bool MULTI>
 __global__ void __launch_bounds__(kFsThreads, NI2 <= 2 ? 4 : 3)
 fwd_occ_kernel(const FsParams p) {
+    const int nq = MULTI ? p.nq : 1;  // compile-time 1 for the single-observer instantiation: its q loop folds away
     if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // dense or clustered input: stencil_fwd_kernel does the work
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_floats = p.RP * p.AS;
@@ -301,11 +306,11 @@ fwd_occ_kernel(const FsParams p) {
     const int acc_floats = (kRZ * plane_floats + p.kx * p.AS + 31) & ~31;
     FsEntry* lists = reinterpret_cast<FsEntry*>(acc + acc_floats);  // [HZ][kFsCap]
     float* sk = reinterpret_cast<float*>(lists + p.HZ * kFsCap);
-    int* cnt = reinterpret_cast<int*>(sk + ((T + 31) & ~31));        // [HZ] non-zeros per halo z-row
+    int* cnt = reinterpret_cast<int*>(sk + ((nq * T + 31) & ~31));  // [HZ] non-zeros per halo z-row
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
-    for (int t = tid; t < T; t += kFsThreads) sk[t] = __ldg(p.Kstar + t);
+    for (int t = tid; t < nq * T; t += kFsThreads) sk[t] = __ldg(p.Kstar + t);
 
     // phase A constants of this lane: its (x-row, 32-column chunk) pair in each iteration
     // (flat voxel indices fit 32 bits: the launcher only picks this kernel below 2^31 - 2^20 voxels)
@@ -363,10 +368,6 @@ fwd_occ_kernel(const FsParams p) {
             tc[2] -= cy ? p.tiles_z : 0;
             tc[3] += ts[3] + cy;
         }
-        {
-            float4* a4 = reinterpret_cast<float4*>(accp);
-            for (int i = lane; i < (plane_floats >> 2); i += 32) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         // live halo columns of this tile (gy = y0 - ply + c inside [0, Y)) and live x-rows, per pair of this lane
         unsigned vm[kFoPairIt];
         {
@@ -380,8 +381,19 @@ fwd_occ_kernel(const FsParams p) {
         }
         // flat index of the halo box origin (z-row 0, x-row 0, column 0); may be negative at the grid's first rows
         const int org = ((b * p.Z + (z0 - p.plz)) * p.X + (x0 - p.plx)) * p.Y + (y0 - ply);
+        // One pass per observer q (nq == 1 outside SCENENetQuantile).  The lists of round 0 serve every q; only a tile
+        // with an overflowing row (more than kFsCap non-zeros: further rounds rewrite the lists) lists again for q > 0.
+        bool multi_round = false;
+        for (int q = 0; q < nq; ++q) {
+        if (q > 0 && multi_round) __syncthreads();  // every warp is done reading the last round's lists of q - 1
+        {
+            float4* a4 = reinterpret_cast<float4*>(accp);
+            for (int i = lane; i < (plane_floats >> 2); i += 32) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         int lo = 0;
         while (true) {
+            int more = 0;
+            if (q == 0 || multi_round) {
             // ---- A: list the non-zero voxels [lo, lo + cap) of every halo z-row from the occupancy bits
             bool my_more = false;
             for (int zr = warp; zr < p.HZ; zr += kFsWarps) {
@@ -436,7 +448,9 @@ fwd_occ_kernel(const FsParams p) {
                 }
                 my_more |= n > lo + kFsCap;
             }
-            const int more = __syncthreads_or(my_more ? 1 : 0);
+            more = __syncthreads_or(my_more ? 1 : 0);
+            if (lo == 0 && more) multi_round = true;
+            }
             // ---- B: warp zo adds slice dz of the taps at every listed voxel of row zo + dz
             for (int dz = 0; dz < p.kz; ++dz) {
                 int n = cnt[warp + dz] - lo;
@@ -444,7 +458,7 @@ fwd_occ_kernel(const FsParams p) {
                 if (n == 0) continue;
                 float kk[NI2];
 #pragma unroll
-                for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[dz * P + 32 * j] : 0.f;
+                for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[q * T + dz * P + 32 * j] : 0.f;
                 // two list entries per 16-byte broadcast load; shared-memory addresses are formed by hand (the generic
                 // C++ form cost 12 instructions per entry, this one 5) and the read-modify-write is predicated, not
                 // branched, so the warp stays converged: its LDS / STS are executed in program order, which is what
@@ -470,7 +484,7 @@ fwd_occ_kernel(const FsParams p) {
         // ---- C: epilogue of this warp's plane (lane -> 4 consecutive y)
         {
             const int gz = z0 + warp;
-            const size_t idx0 = (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
+            const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
                 const int g = lane + 32 * i;
@@ -518,12 +532,13 @@ fwd_occ_kernel(const FsParams p) {
                 }
             }
         }
+        }  // q
         __syncthreads();  // lists and counts are rewritten by the next tile
     }
 }
 
 // geometry; false when the kernel does not cover the shape (caller uses the dense stencil)
-static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, FsParams& p, size_t& smem, int& ni2) {
+static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, FsParams& p, size_t& smem, int& ni2, int nq = 1) {
     p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx; p.ky = ky;
     const int P = kx * ky;
     ni2 = ceil_div(P, 32);
@@ -552,7 +567,7 @@ static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, 
     const int T = kz * P;
     const size_t accb = (size_t)((kRZ * p.RP * p.AS + kx * p.AS + 31) & ~31) * 4;
     const size_t lst = (size_t)p.HZ * kFsCap * sizeof(FsEntry);
-    const size_t taps = (size_t)((T + 31) & ~31) * 4;
+    const size_t taps = (size_t)((nq * T + 31) & ~31) * 4;
     const size_t cntb = (size_t)((p.HZ + 1) & ~1) * 4;
     const size_t scanb = (size_t)ceil_div(p.HX * p.WS / 4, 32) * 32 * 16;
     smem = accb + lst + scanb + taps + cntb + 16;
@@ -572,7 +587,10 @@ static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
     // 32-bit flat voxel indices (incl. the halo overshoot)
     const bool occ = p.mask && p.HX * ((p.IY + p.ky - 1 + 31) >> 5) <= kFoPairIt * 32 && p.IX * p.IY == 512 &&
                      (long long)p.B * p.Z * p.X * p.Y < (1ll << 31) - (1ll << 20);
-    auto kern = occ ? (p.out_f64 ? fwd_occ_kernel<NI2, true> : fwd_occ_kernel<NI2, false>) : fwd_sparse_kernel<NI2>;
+    if (p.nq > 1 && !occ) return SN_ERR_UNSUPPORTED;  // only the mask-driven kernel shares its lists between observers
+    auto kern = !occ ? fwd_sparse_kernel<NI2>
+                : p.nq > 1 ? (p.out_f64 ? fwd_occ_kernel<NI2, true, true> : fwd_occ_kernel<NI2, false, true>)
+                           : (p.out_f64 ? fwd_occ_kernel<NI2, true, false> : fwd_occ_kernel<NI2, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -585,11 +603,13 @@ static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
 
 int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
                       unsigned long long nnz_max, unsigned long long dw_max, const unsigned* occ_mask, int B, int Z, int X, int Y,
-                      int kz, int kx, int ky, cudaStream_t stream) {
+                      int kz, int kx, int ky, int nq, cudaStream_t stream) {
     FsParams p{};
     size_t smem;
     int ni2;
-    if (!plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2)) return SN_ERR_UNSUPPORTED;
+    if (nq < 1 || !plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2, nq)) return SN_ERR_UNSUPPORTED;
+    p.nq = nq;
+    p.pred_qstride = (long long)B * Z * X * Y;
     p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = nnz; p.nnz_max = nnz_max; p.dw_max = dw_max;
     p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
     {

@@ -283,6 +283,25 @@ def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype,
     return pred
 
 
+def scenenet_fwd_multi(x32: torch.Tensor, Kstars: torch.Tensor, out_dtype: torch.dtype, nnz: Optional[torch.Tensor] = None,
+                       mode: int = 0) -> torch.Tensor:
+    """several observers on the same grids (SCENENetQuantile): Kstars [Q,kz,kx,ky] float32 -> preds [Q,B,1,Z,X,Y];
+    with the grid state `nnz` the occupancy-driven kernel lists the non-zero voxels once for all Q tap sets."""
+    _need_cuda(x32, "x")
+    B, Z, X, Y = _grid_dims(x32)
+    if Kstars.dim() != 4 or Kstars.dtype != torch.float32:
+        raise TypeError("Kstars must be float32 [Q, kz, kx, ky]")
+    Kstars = Kstars.contiguous()
+    Q, kz, kx, ky = (int(v) for v in Kstars.shape)
+    preds = torch.empty((Q, *x32.shape), dtype=out_dtype, device=x32.device)
+    if x32.numel() == 0:
+        return preds
+    with _on_device(x32.device):
+        check(lib.sn_scenenet_fwd_multi(x32.data_ptr(), _ptr(nnz), int(mode), Kstars.data_ptr(), Q, B, Z, X, Y, kz, kx, ky,
+                                        preds.data_ptr(), _DT[out_dtype], _stream()), "sn_scenenet_fwd_multi")
+    return preds
+
+
 _ws_cache: dict = {}
 
 

@@ -30,6 +30,7 @@ def test_argument_validation_without_gpu():
     """error paths return codes before any CUDA call"""
     from scenenet_b200._lib import lib
     assert lib.sn_scenenet_fwd(None, None, 0, None, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
+    assert lib.sn_scenenet_fwd_multi(None, None, 0, None, 3, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
     assert lib.sn_cast_f64_to_f32(None, None, 4, None) == -1
     assert lib.sn_threshold(None, 0, 0.5, 4, None, None) == -1
     assert lib.sn_scenenet_bwd_workspace_bytes(0, 8, 8, 8, 3, 3, 3) == -1

@@ -104,3 +104,41 @@ def test_clustered_grids_go_to_the_dense_stencil():
         assert torch.equal(auto, forced)
         other = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=3 - want)
         assert float((auto - other).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "dense", "float32", "overflow"])
+def test_quantile_model_one_forward_for_all_observers(case):
+    """SCENENetQuantile inference (SCENE_Net.py:409-415) through sn_scenenet_fwd_multi against the per-observer path
+    (taken when gradients are required): identical values; and the C entry point against single-observer calls"""
+    import scenenet_b200 as sb
+    ops = _ops()
+    torch.manual_seed(3)
+    qnet = sb.SCENENetQuantile({'cy': 1, 'cone': 1, 'neg': 1}, (9, 5, 5), qs=torch.tensor([0.1, 0.5, 0.9]), device=torch.device(DEV))
+    g = torch.Generator(device=DEV).manual_seed(4)
+    shape = (2, 1, 32, 32, 64)
+    if case == "clustered":
+        x = torch.zeros(shape, dtype=torch.float64, device=DEV)
+        x[:, :, 10:12] = (torch.rand((2, 1, 2, 32, 64), generator=g, device=DEV) < 0.5).double()
+    elif case == "overflow":  # sparse overall, but rows with more than 128 non-zeros: several list rounds per tile
+        x = torch.zeros(shape, dtype=torch.float64, device=DEV)
+        x[:, :, 10, 4:8] = 1.0
+        x[:, :, 20, 12:14, ::2] = 1.0
+    else:
+        x = (torch.rand(shape, generator=g, device=DEV) < (0.3 if case == "dense" else 0.02)).double()
+    if case == "float32":
+        x = x.float()
+    per_net = qnet(x)                       # gradients enabled: one observer after the other
+    with torch.no_grad():
+        fused = qnet(x)
+    assert fused.shape == per_net.shape == (2, 3, 32, 32, 64) and fused.dtype == torch.float32
+    assert torch.equal(fused, per_net.detach())
+    # the entry point itself, every mode, against single-observer launches
+    x32, st = ops.prepare(x)
+    Ks = torch.randn((3, 9, 5, 5), generator=g, device=DEV) * 0.2
+    for mode in (0, 1, 2):
+        multi = ops.scenenet_fwd_multi(x32, Ks, torch.float64, nnz=st, mode=mode)
+        for q in range(3):
+            assert torch.equal(multi[q], ops.scenenet_fwd(x32, Ks[q], torch.float64, nnz=st, mode=mode)), (case, mode, q)
+    no_state = ops.scenenet_fwd_multi(x32, Ks, torch.float32, mode=2)  # no state buffer: scanning kernel, one launch each
+    for q in range(3):
+        assert torch.equal(no_state[q], ops.scenenet_fwd(x32, Ks[q], torch.float32, mode=2))
