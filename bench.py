@@ -212,46 +212,86 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
-def cpu_step_fn(batch):
-    """The oracle port of the reference's CPU path: float64 conv3d + autograd, all host threads."""
-    from oracle import model_oracle as mo
-    torch.set_num_threads(os.cpu_count() or 1)
-    model = mo.kat_model(KERNEL)
-    x, _ = mo.synthetic_grids(batch, GRID, seed=1234)
-    dpred = torch.randn(x.shape, generator=torch.Generator().manual_seed(1235), dtype=torch.float64)
-
+CPU_ARM_SRC = r"""
+import json, os, sys, time
+sys.path.insert(0, {root!r})
+import torch
+assert not torch.cuda.is_available()
+torch.set_num_threads(os.cpu_count() or 1)
+from oracle import model_oracle as mo
+batch, steps, warmup, kernel, grid, use_ref, budget_s = {batch}, {steps}, {warmup}, {kernel!r}, {grid!r}, {use_ref}, {budget_s}
+x, _ = mo.synthetic_grids(batch, grid, seed=1234)
+dpred = torch.randn(x.shape, generator=torch.Generator().manual_seed(1235), dtype=torch.float64)
+if use_ref:
+    # the UNMODIFIED reference: core/models/SCENE_Net.py SceneNet.forward (float64 conv3d of G kernels + observer) and
+    # autograd's backward onto the 11 trainable scalars, on the host cores
+    from oracle import ref_shim
+    m = ref_shim.reference_scenenet(mo.KAT_GENEO_NUM, kernel, mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST)
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        m(x).backward(dpred)
+else:
+    model = mo.kat_model(kernel)
     def step():
         mo.fwd_bwd(model, x, None, dpred)
-    return step
+tw = time.perf_counter()
+for i in range(warmup):
+    step()
+    if i >= 0 and time.perf_counter() - tw > 0.25 * budget_s:
+        break
+t0 = time.perf_counter()
+done = 0
+while done < steps:
+    step()
+    done += 1
+    if done >= 2 and (time.perf_counter() - t0) * (done + 1) / done > budget_s:
+        break  # bounded: the arm must end within a few minutes on any host
+dt = time.perf_counter() - t0
+print("CPU_ARM " + json.dumps(dict(grids_per_s=batch * done / dt, s_per_step=dt / done, threads=torch.get_num_threads(),
+                                   kind="reference" if use_ref else "port", steps_timed=done)))
+"""
 
 
-def time_cpu(batch, steps, warmup):
-    step = cpu_step_fn(batch)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+def time_cpu(batch, steps, warmup, timeout=1500, budget_s=200.0):
+    """fwd+bwd of config 2 on the host cores, in a child process that cannot see the GPU (the reference pins its
+    kernels to CUDA whenever a GPU is visible, core/models/geneos/*.py): the REAL reference (`/root/reference` in the
+    build container, its unmodified copy `oracle/_ref` on the GPU box — oracle/fetch_ref.py) when the tree is present,
+    else the oracle port.  Returns (grids/s, s/step, threads, kind)."""
+    from oracle import ref_shim
+    src = CPU_ARM_SRC.format(root=ROOT, batch=batch, steps=steps, warmup=warmup, kernel=tuple(KERNEL), grid=tuple(GRID),
+                             use_ref=bool(ref_shim.available()), budget_s=float(budget_s))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONWARNINGS="ignore")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", src], env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    for ln in r.stdout.splitlines():
+        if ln.startswith("CPU_ARM "):
+            d = json.loads(ln[8:])
+            return d["grids_per_s"], d["s_per_step"], d["threads"], d["kind"], d["steps_timed"]
+    raise RuntimeError(f"CPU arm failed: {r.stdout[-1000:]} {r.stderr[-3000:]}")
+
+
+def cpu_sample_note(batch, kind):
+    what = ("the UNMODIFIED reference (core/models/SCENE_Net.py SceneNet fwd + autograd bwd, float64 conv3d, its copy oracle/_ref)"
+            if kind == "reference" else "oracle port of the reference's float64 PyTorch CPU path (reference tree absent on this box)")
+    whole = " (the whole config-2 batch)" if batch == B_PER_GPU else ""
+    return f"{batch} of {B_PER_GPU} grids per step{whole}, {what}, all host threads"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2
-    v, per_step = time_cpu(batch, args.steps, args.warmup)
-    cores = torch.get_num_threads()
+    batch = args.cpu_batch or B_PER_GPU  # the same config as the CUDA arm: 32 grids per step
+    v, per_step, cores, kind, timed = time_cpu(batch, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SCENE-Net training step fwd+bwd, synthetic TS40K-shaped 64^3 grids, kernel (9,5,5), G=3 "
-                               f"(BASELINE config 2); CPU step = bounded sample of {batch} grids of the 32-grid batch"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{batch} of 32 grids per step, oracle port of the reference's float64 PyTorch CPU path "
-                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "config": {"workload": "SCENE-Net training step fwd+bwd (13 params, 11 trainable), batch 32 of synthetic TS40K-shaped 64^3 "
+                               "occupancy grids (Bernoulli 0.016), kernel (9,5,5), G=3, fixed upstream dL/dpred ~ N(0,1) (BASELINE "
+                               "config 2); the reference's own CPU path on the host cores",
+                   "global_batch": batch, "same_config_as_cuda_arm": batch == B_PER_GPU},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_note(batch, kind)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -372,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--io-dtype", default="f64", choices=["f64", "f32"], help="dtype of x / dpred / pred at the module boundary")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="grids per CPU step of the reference arm (default: the whole batch of 32; "
+                                                             "smaller values are for quick self-tests and are reported as a sample)")
     ap.add_argument("--eager", action="store_true", help="time the eager module path instead of CUDA-graph replays")
     ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"],
                     help="config2 = the headline (default); config4 = 128^3 grids, cubic kernel --kernel, batch 8 per GPU; "
@@ -738,9 +780,9 @@ def main():
         })
         vox = voxel_bench(device, hbm_gbs) if args.workload == "config2" else None
         if not args.no_cpu_baseline and world == 1:
-            v, per = time_cpu(2, 3, 1)
-            cpu_base = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": "2 of the 32 grids, 1 warm-up + 3 timed fwd+bwd steps of the oracle port (float64 conv3d + autograd)"}
+            v, per, cores, kind, _ = time_cpu(B_PER_GPU, 4, 1, budget_s=45.0)
+            cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "s_per_step": per,
+                        "sample": cpu_sample_note(B_PER_GPU, kind) + "; 1 warm-up + up to 4 timed steps (at most ~45 s)"}
 
     if rank == 0:
         if roof is not None:

@@ -1,0 +1,142 @@
+"""The drop-in claim of BASELINE.json's north_star, proven with the reference's OWN code on the GPU box:
+"the lit_modules training loop and criterions run unchanged".
+
+The reference tree travels as `oracle/_ref` (unmodified copy made by `oracle/fetch_ref.py`, git-ignored, shipped by
+gpurun).  Ground truth = the unmodified reference on the host CPU, in a child process that cannot see the GPU (the
+reference pins its kernels to CUDA whenever one is visible).  Under test = the reference's unchanged
+`GENEO_Tversky_Loss` (core/criterions/geneo_loss.py:145-166), `LitSceneNet.training_step` + optimizers
+(core/lit_modules/lit_model_wrappers.py:136-174) and Lightning checkpoints over `scenenet_b200.SceneNet`.
+Bars: pred max-norm 1e-5, loss 1e-5, each of the 11 gradients 1e-5 relative (north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo, ref_runner, ref_shim
+
+pytestmark = [pytest.mark.gpu, pytest.mark.reference]
+DEV = "cuda"
+RTOL = 1e-5
+
+
+def _sb():
+    import scenenet_b200 as sb
+    return sb
+
+
+def _x575(golden_dir):
+    v = np.load(os.path.join(golden_dir, "vox_sample_575.npz"))
+    x = np.zeros(64 ** 3)
+    x[v["restated_density_idx"]] = 1.0
+    y = np.zeros(64 ** 3)
+    y[v["ref_frac_idx"]] = 1.0
+    return torch.from_numpy(x).view(1, 1, 64, 64, 64), torch.from_numpy(y).view(1, 1, 64, 64, 64)
+
+
+def _check_grads(got, ref, rtol=RTOL):
+    worst = 0.0
+    for n, r in ref.items():
+        if r is None:
+            assert got[n] is None, n
+            continue
+        assert got[n] is not None, n
+        rel = abs(got[n] - r) / max(abs(r), 1e-30)
+        worst = max(worst, rel)
+        assert rel <= rtol or abs(got[n] - r) <= 1e-12, (n, got[n], r, rel)
+    return worst
+
+
+CKPT_PARAMS = None
+
+
+def _ckpt_vector():
+    sd, _ = ref_shim.load_lightning_state_dict("FBetaScore.ckpt")
+    params = {k.replace("geneos.", "").replace(".geneo_params", ""): float(v) for k, v in sd.items() if k.startswith("geneos.")}
+    lambdas = {k.replace("lambdas_dict.", ""): float(v) for k, v in sd.items() if k.startswith("lambdas_dict.")}
+    return params, lambdas
+
+
+@pytest.mark.parametrize("case", ["kat575", "ckpt575", "syn_b2_64", "kat_9x7x7"])
+def test_reference_criterion_class_runs_unchanged_on_cuda_model(golden_dir, case):
+    if case == "kat575":
+        (x, y), ks, (params, lambdas), last = _x575(golden_dir), (9, 5, 5), (mo.KAT_PARAMS, mo.KAT_LAMBDAS), mo.KAT_LAST
+    elif case == "ckpt575":
+        (x, y), ks, (params, lambdas), last = _x575(golden_dir), (9, 5, 5), _ckpt_vector(), "lambda_cy_0"
+    elif case == "syn_b2_64":
+        (x, y), ks, (params, lambdas), last = mo.synthetic_grids(2, (64, 64, 64), seed=77), (9, 5, 5), (mo.KAT_PARAMS, mo.KAT_LAMBDAS), "lambda_neg_0"
+    else:
+        (x, y), ks, (params, lambdas), last = mo.synthetic_grids(2, (32, 32, 32), seed=78, p_gt=3e-3), (9, 7, 7), (mo.KAT_PARAMS, mo.KAT_LAMBDAS), mo.KAT_LAST
+    job = dict(kind="criterion_step", geneo_num=mo.KAT_GENEO_NUM, ks=list(ks), params=params, lambdas=lambdas, last=last)
+    meta, out = ref_runner.run_cpu_subprocess(job, dict(x=x.numpy(), y=y.numpy()))
+    pred, loss, grads, m = ref_runner.criterion_step(x, y, mo.KAT_GENEO_NUM, ks, params, lambdas, last, device=DEV,
+                                                     scenenet_cls=_sb().SceneNet)
+    assert type(m).__module__.startswith("scenenet_b200") and pred.is_cuda and pred.dtype == torch.float64
+    ref = out["pred"]
+    err = np.abs(pred.cpu().numpy() - ref).max()
+    assert err <= RTOL * np.abs(ref).max(), (err, np.abs(ref).max())
+    assert abs(loss - meta["loss"]) <= RTOL * abs(meta["loss"]), (loss, meta["loss"])
+    worst = _check_grads(grads, meta["grads"])
+    print(f"{case}: reference GENEO_Tversky_Loss over the CUDA model: loss rel {abs(loss - meta['loss']) / abs(meta['loss']):.2e}, "
+          f"worst grad rel {worst:.2e}")
+
+
+def test_reference_scenenet_on_its_own_gpu_path_agrees(golden_dir):
+    """the reference run the way its authors ran it (model on CUDA, float64 cuDNN/ATen conv3d) against ours"""
+    x, y = _x575(golden_dir)
+    pr, lr_, gr, _ = ref_runner.criterion_step(x, y, mo.KAT_GENEO_NUM, (9, 5, 5), mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST, device=DEV)
+    pred, loss, grads, _ = ref_runner.criterion_step(x, y, mo.KAT_GENEO_NUM, (9, 5, 5), mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST,
+                                                     device=DEV, scenenet_cls=_sb().SceneNet)
+    assert float((pred - pr).abs().max()) <= RTOL * float(pr.abs().max())
+    assert abs(loss - lr_) <= RTOL * abs(lr_)
+    _check_grads(grads, gr)
+
+
+@pytest.mark.parametrize("optimizer,lr", [("sgd", 1e-3), ("adam", 1e-3)])
+def test_lit_scenenet_training_steps_unchanged(golden_dir, optimizer, lr):
+    """LitSceneNet.__init__ builds the model from the swapped-in class; three optimizer steps on two batches"""
+    sb = _sb()
+    b0 = _x575(golden_dir)
+    b1 = mo.synthetic_grids(1, (64, 64, 64), seed=5, p_gt=1e-3)
+    n_steps = 3
+    init = (mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST)
+    job = dict(kind="lit", geneo_num=mo.KAT_GENEO_NUM, ks=[9, 5, 5], n_steps=n_steps, lr=lr, optimizer=optimizer,
+               params=init[0], lambdas=init[1], last=init[2])
+    meta, _ = ref_runner.run_cpu_subprocess(job, dict(x=np.stack([b0[0].numpy(), b1[0].numpy()]), y=np.stack([b0[1].numpy(), b1[1].numpy()])))
+    from scenenet_b200.utils.scripts_utils import init_metrics
+    losses, values, lit = ref_runner.lit_training_steps([b0, b1], mo.KAT_GENEO_NUM, (9, 5, 5), n_steps, lr, optimizer, device=DEV,
+                                                        scenenet_cls=sb.SceneNet, metric_initializer=init_metrics, init=init)
+    assert isinstance(lit.model, sb.SceneNet) and type(lit).__module__ == "core.lit_modules.lit_model_wrappers"
+    assert lit.model.last_lambda == meta["last_lambda"]
+    for a, b in zip(losses, meta["losses"]):
+        assert abs(a - b) <= RTOL * abs(b), (losses, meta["losses"])
+    for n, v in meta["values"].items():
+        # parameters after the optimizer steps: float32 values; Adam normalises the step, so gradient noise at the 1e-6
+        # level moves a parameter by <= lr * 1e-5 per step
+        assert abs(values[n] - v) <= 2e-6 * max(1.0, abs(v)), (n, values[n], v)
+    assert "train_loss" in lit.logged
+    res = lit.train_metrics.compute()  # the metric collection was fed by training_step (lit_model_wrappers.py:170-171)
+    assert set(res) == {"JaccardIndex", "Precision", "Recall", "F1Score", "FBetaScore"}
+    print(f"LitSceneNet/{optimizer}: losses {losses} vs reference {meta['losses']}")
+
+
+@pytest.mark.parametrize("name", ["FBetaScore.ckpt", "last.ckpt"])
+def test_lightning_checkpoint_loads_into_cuda_model(golden_dir, name):
+    x, _ = _x575(golden_dir)
+    meta, out = ref_runner.run_cpu_subprocess(dict(kind="ckpt", name=name), dict(x=x.numpy()))
+    pred, m, missing = ref_runner.checkpoint_forward(x, name, device=DEV, scenenet_cls=_sb().SceneNet)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    vals = {n: float(p.detach()) for n, p in m.named_parameters()}
+    assert m.last_lambda == meta["last_lambda"]
+    for n, v in meta["values"].items():  # incl. the last-lambda side effect of forward (SCENE_Net.py:333)
+        assert vals[n] == v, (n, vals[n], v)
+    ref = out["pred"]
+    p = pred.cpu().numpy()
+    assert np.abs(p - ref).max() <= RTOL * np.abs(ref).max()
+    # threshold 0.65 (prob_to_label): identical labels away from the threshold
+    from scenenet_b200.utils import voxelization as Vox
+    lab = Vox.prob_to_label(pred, 0.65).cpu().numpy()
+    safe = np.abs(ref - 0.65) > 1e-5
+    assert np.array_equal(lab[safe], (ref >= 0.65).astype(ref.dtype)[safe])
+    assert int((lab != (ref >= 0.65)).sum()) <= 2
