@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 3
+#define SN_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define SN_OK 0
@@ -96,6 +96,11 @@ int64_t sn_launch_count(void);
  *   Kstar      [T]   float32 out  — sum_g lambda_eff[g] * K[g] (accumulated in float64): by
  *                                   linearity of the convolution the observer's
  *                                   sum_g lambda_g * conv3d(x, K_g) equals conv3d(x, Kstar)
+ *   Kstar64    [T+1] float64 out (NULL to skip; ABI v4) — the same sums NOT rounded to float32, followed by
+ *                                   sum_t |Kstar64[t]|: the forward kernels re-evaluate a voxel whose float32 sum is
+ *                                   within rounding distance of zero with these taps in float64, so that the relu gate
+ *                                   [s > 0] (and with it the whole gradient of that voxel) agrees with the reference's
+ *                                   float64 convolution (SCENE_Net.py:325)
  *   write_last_lambda != 0: also stores lambda_eff[last] into the last-lambda parameter
  *                                   (the side effect of SCENE_Net.py:333)
  *   param_snapshot [n_param_ptrs] float32 out (NULL to skip) — the parameter values this
@@ -104,7 +109,7 @@ int64_t sn_launch_count(void);
  * lambda_eff / Kstar may be NULL when desc->lambda_index[0] < 0 (bare GENEO kernels).
  * ====================================================================================== */
 int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const* param_ptrs_host,
-                       float* K, float* lambda_eff, float* Kstar, float* param_snapshot,
+                       float* K, float* lambda_eff, float* Kstar, double* Kstar64, float* param_snapshot,
                        int write_last_lambda, void* stream);
 
 /* Jacobian^T of the synthesis: dparams[i] = sum_{g,t} dK[g,t] * dK_g[t]/dparam_i for every
@@ -126,28 +131,35 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
  * Observer forward — replaces F.conv3d + convex combination + relu(tanh) of
  * SceneNet.forward / SCENE_Net.forward (SCENE_Net.py:209-226, 322-339).
  *   x     [B,1,Z,X,Y] float32          (sn_grid_prepare converts the reference's float64 grids)
- *   nnz   DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count + occupancy bits), or NULL
- *   mode  SN_PATH_AUTO: with nnz, the dense stencil and an occupancy-driven kernel (cost proportional to the
- *         occupied voxels) are both enqueued and the count selects ON THE DEVICE which of them works (sparse up
- *         to 3 % occupancy for kx*ky <= 64 taps per slice, 4 % above, and only for grids that are not clustered:
- *         sn_select_fwd_path_state); without nnz the dense stencil runs.  SN_PATH_DENSE / SN_PATH_SPARSE force one
- *         (measurement, tests).  Same pred either way up to float32 summation order.
- *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
+ *   nnz   DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (counters, occupancy bits, tile list),
+ *         or NULL
+ *   mode  SN_PATH_AUTO: with nnz, the occupancy-driven kernel (cost proportional to the occupied voxels) walks the
+ *         tiles first and decides PER TILE, on the device, from the tile's own occupancy: empty tiles are zero-filled,
+ *         sparse tiles are scattered, tiles above the break-even occupancy are appended to the tile list in the state
+ *         buffer and the dense stencil, enqueued right behind, computes exactly those (no host synchronisation; shapes
+ *         without a dense instantiation or with more tiles than the list holds fall back to one device-side choice
+ *         for the whole grid, sn_select_fwd_path_state).  Without nnz the dense stencil runs.
+ *         SN_PATH_DENSE / SN_PATH_SPARSE force one kernel for every tile (measurement, tests).  Same pred either way up
+ *         to float32 summation order.
+ *   Kstar [T] float32, Kstar64 [T+1] float64 or NULL   (from sn_geneo_synth_fwd; with Kstar64 the sign of sums within
+ *         float32 rounding distance of zero is decided in float64 — see there)
  *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
  * x must be 16-byte aligned.
  * ====================================================================================== */
 #define SN_PATH_AUTO 0
 #define SN_PATH_DENSE 1
 #define SN_PATH_SPARSE 2
-int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
+int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, const double* Kstar64,
                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype, void* stream);
 /* Several observers on the SAME grids — SCENENetQuantile.forward (SCENE_Net.py:409-415: one SCENE_Net per quantile,
- * predictions concatenated).  Kstars [n_observers][T] float32, preds [n_observers][B,1,Z,X,Y] out.
+ * predictions concatenated).  Kstars [n_observers][T] float32, Kstars64 [n_observers][T+1] float64 or
+ * NULL, preds [n_observers][B,1,Z,X,Y] out.
  * The occupancy-driven kernel lists the non-zero voxels of a tile once and scatters them with every observer's taps
  * (x is read once); the dense stencil runs once per observer.  Selection as in sn_scenenet_fwd.  n_observers <= 8. */
 #define SN_MAX_OBSERVERS 8
-int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, int n_observers,
-                          int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype, void* stream);
+int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, const double* Kstars64,
+                          int n_observers, int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype,
+                          void* stream);
 
 /* Observer backward, data part — replaces aten::convolution_backward (weight gradient) and
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
@@ -168,12 +180,15 @@ int sn_scenenet_bwd(const float* x, const unsigned long long* nnz, int mode, con
                     double* W, void* ws, int64_t ws_bytes, void* stream);
 /* The selection rule of SN_PATH_AUTO for a host that already knows the occupancy (a step captured once for replay on
  * grids of one kind can then enqueue only the kernel that will work; both kernels are correct at ANY occupancy, the
- * choice only affects speed).  which: 0 = forward, 1 = tap gradient.  Returns SN_PATH_DENSE / SN_PATH_SPARSE. */
+ * choice only affects speed).  which: 0 = forward, 1 = tap gradient.  Returns SN_PATH_DENSE / SN_PATH_SPARSE (forward
+ * also SN_PATH_AUTO, see sn_select_fwd_path_state). */
 int sn_select_path(int which, int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
 int sn_select_fwd_path(int64_t nnz, int B, int Z, int X, int Y, int kz, int kx, int ky);
 /* The forward's rule with the clustering statistic of the state buffer (state[2] = mask words with >= 8 of 32 voxels
- * occupied): a sparse but CLUSTERED grid (a locally dense layer, e.g. the ground of a LiDAR scan) goes to the dense
- * stencil, because the occupancy-driven kernel's cost per tile follows the tile's own occupancy. */
+ * occupied): SN_PATH_SPARSE for a uniformly sparse grid (every tile is scattered; no stencil pass is needed),
+ * SN_PATH_AUTO (the per-tile choice of sn_scenenet_fwd) for a sparse but CLUSTERED grid (a locally dense layer, e.g. the
+ * ground of a LiDAR scan) or a moderately occupied one (<= 25 %), SN_PATH_DENSE above that or where tiles cannot be
+ * handed over. */
 int sn_select_fwd_path_state(int64_t nnz, int64_t dense_words, int B, int Z, int X, int Y, int kz, int kx, int ky);
 
 /* The two passes of sn_scenenet_bwd, callable on their own (measurement, fused criterions that
@@ -238,13 +253,19 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
 /* Grid preparation, one HBM pass: x (SN_F64 as handed over by the reference's ToTensor, torch_transforms.py:13;
  * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
  * nothing is copied) and the grid STATE buffer `nnz` the forward / backward take:
- *   [0] uint64 number of non-zero voxels, [1] uint64 ticket counter the tap-gradient kernels use to let their last
- *   CTA sum the partial rows (so one sn_grid_prepare call serves exactly one forward + one backward), [2] uint64 number
- *   of 32-voxel mask words with >= 8 voxels occupied (how clustered the grid is), [3] reserved, then from
- *   byte 32 one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel index i; ABI v3): the
- *   occupancy-driven forward lists the non-zero voxels of a halo row from these words instead of scanning floats.
+ *   SN_STATE_WORDS uint64 counters — [0] number of non-zero voxels, [1] ticket counter the tap-gradient kernels use to let
+ *   their last CTA sum the partial rows, [2] number of 32-voxel mask words with >= 8 voxels occupied (how clustered the
+ *   grid is), [3] number of tiles the occupancy-driven forward handed to the dense stencil, [4] number of non-zero voxels
+ *   whose value is not 1 (0 <=> an occupancy grid: the forward then takes its values from the mask bits), [5] tile
+ *   counter of the occupancy-driven forward (dynamic tile scheduling), [6] CTA-done counter of the dense stencil's
+ *   tile-list pass, [7] reserved; the kernels that use [1], [3], [5], [6] leave them at zero again, so one call serves
+ *   any number of forwards / backwards that follow each other on a stream —
+ *   then from byte 8 * SN_STATE_WORDS one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel
+ *   index i) + 4 padding words: the occupancy-driven forward lists the non-zero voxels of a halo box from these words
+ *   instead of scanning floats — then the tile list ([3] entries, 32-bit tile ids; ABI v4).
  * nnz: DEVICE buffer of sn_grid_state_bytes(n) bytes, 16-byte aligned; counters zeroed and bits written by the call.
  * x and x32 16-byte aligned. */
+#define SN_STATE_WORDS 8
 int64_t sn_grid_state_bytes(int64_t n);
 int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream);
 /* float64 -> float32 (callers hand float64 grids: torch_transforms.py:13) */

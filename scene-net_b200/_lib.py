@@ -20,7 +20,7 @@ SN_MAX_PARAM_PTRS = 96
 SN_MAX_TAPS = 4096
 SN_CRIT_MAX_BINS = 12
 SN_CRIT_COEF = SN_CRIT_MAX_BINS + 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 KIND = {
     "cylinder_kernel": 0, "cylinderv2": 1, "cone_kernel": 2, "arrow": 3, "neg_sphere_kernel": 4, "negSpherev2": 5,
@@ -50,11 +50,11 @@ SIGNATURES = {
     "sn_abi_version": (_i, []),
     "sn_build_info": (C.c_char_p, []),
     "sn_launch_count": (_i64, []),
-    "sn_geneo_synth_fwd": (_i, [_descp, _pp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sn_geneo_synth_fwd": (_i, [_descp, _pp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sn_geneo_synth_bwd": (_i, [_descp, _pp, _vp, _vp, _vp]),
     "sn_scenenet_param_grads": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _vp]),
-    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "sn_scenenet_fwd_multi": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd_multi": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_select_path": (_i, [_i, _i64, _i, _i, _i, _i, _i, _i, _i]),

@@ -395,7 +395,9 @@ class SCENENetQuantile(nn.Module):
             out_dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
             modes = {tuple(net.path_modes) for net in nets}
             mode = modes.pop()[0] if len(modes) == 1 else 0
-            preds = ops.scenenet_fwd_multi(x32, torch.stack(kstars), out_dtype, nnz=state, mode=mode)  # [Q,B,1,Z,X,Y]
+            k64s = torch.stack([k.k64 for k in kstars]) if all(getattr(k, "k64", None) is not None for k in kstars) else None
+            preds = ops.scenenet_fwd_multi(x32, torch.stack([k.as_subclass(torch.Tensor) for k in kstars]), out_dtype, nnz=state,
+                                           mode=mode, k64s=k64s)  # [Q,B,1,Z,X,Y]
             return preds[:, :, 0].permute(1, 0, 2, 3, 4).to(torch.float32).contiguous()
         return torch.cat([net(x, _prepared=prepared).to(torch.float32) for net in nets], dim=1)
 
@@ -429,5 +431,17 @@ class SCENE_Net_Class(nn.Module):
     def get_dict_parameters(self):
         return dict([(n, param.data.item()) for n, param in self.gnet.named_parameters()])
 
+    def _tau_host(self) -> float:
+        """host copy of tau, refreshed only when the parameter is rewritten (an optimizer step, load_state_dict):
+        `float(self.tau)` on every forward would be a device synchronisation (the reference compares on the device,
+        SCENE_Net.py:465-466); same caching as `_apex_int`"""
+        p = self.tau
+        key = (p.data_ptr(), p._version)
+        cached = self.__dict__.get('_tau_cache')
+        if cached is None or cached[0] != key:
+            cached = (key, float(p.detach()))
+            self.__dict__['_tau_cache'] = cached
+        return cached[1]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.threshold(self.gnet(x), float(self.tau)).to(x.dtype)
+        return ops.threshold(self.gnet(x), self._tau_host()).to(x.dtype)

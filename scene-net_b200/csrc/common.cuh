@@ -2,22 +2,40 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <atomic>
 #include "../../include/scenenet_b200.h"
 
 namespace sn {
 
-extern long long g_launch_count;  // bumped by every launch wrapper (sn_launch_count())
+// bumped by every launch wrapper (sn_launch_count()); the only mutable global of the library — a relaxed atomic, so the
+// entry points stay callable from any host thread
+extern std::atomic<long long> g_launch_count;
+
+// Measurement / debugging switches read from the environment exist only in -DSN_DEBUG builds: a release library never
+// looks at the environment, so no variable can change which kernel runs or what it computes.
+#ifdef SN_DEBUG
+#define SN_ENV(name) getenv(name)
+#else
+#define SN_ENV(name) (static_cast<const char*>(nullptr))
+#endif
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SN_OK : (SN_ERR_CUDA_BASE - (int)e); }
 
 #define SN_LAUNCH_CHECK()                                   \
     do {                                                    \
-        ::sn::g_launch_count++;                             \
+        ::sn::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
         cudaError_t _e = cudaGetLastError();                \
         if (_e != cudaSuccess) return ::sn::cuda_rc(_e);    \
     } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Layout of the grid state buffer behind the SN_STATE_WORDS counters (sn_grid_state_bytes): mask words, then tile ids.
+__host__ __device__ inline long long state_mask_words(long long n) { return (n + 31) / 32 + 4; }
+// capacity of the dense-tile list: every shape whose forward tiles hold >= 1024 voxels on average fits (a 64^3 grid has
+// 64 tiles of 4096 voxels); smaller / ragged shapes with more tiles than this keep every tile in the occupancy kernel
+__host__ __device__ inline long long state_tile_cap(long long n) { return n / 1024 + 1024; }
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div64(long long a, long long b) { return (a + b - 1) / b; }

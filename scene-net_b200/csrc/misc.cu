@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace sn {
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 // float64 -> float32, 2 doubles per thread per step (16-byte loads), grid-stride
 __global__ void __launch_bounds__(256) cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
@@ -37,25 +37,31 @@ __global__ void __launch_bounds__(256) cast_u8_f32_kernel(const unsigned char* _
 // the non-zero voxels of a halo row with one 64-bit load instead of scanning the floats).  Integer atomics only: the
 // count is exact and order-independent.
 // (one atomic per CTA: thousands of same-address atomics at the end of the kernel were a visible serial tail)
-// cnt -> nnz[0] (non-zero voxels), dense -> nnz[2] (mask words with >= kDenseWordBits bits set: how clustered the grid is)
-__device__ __forceinline__ void add_count(unsigned cnt, unsigned dense, unsigned long long* nnz) {
-    __shared__ unsigned s_cnt[8], s_dns[8];
+// cnt -> nnz[0] (non-zero voxels), dense -> nnz[2] (mask words with >= kDenseWordBits bits set: how clustered the grid is),
+// nonunit -> nnz[4] (non-zero voxels whose value is not 1: zero for the occupancy grids ToFullDense hands over, and then
+// the occupancy-driven forward takes the value 1 from the mask bit instead of loading x)
+__device__ __forceinline__ void add_count(unsigned cnt, unsigned dense, unsigned nonunit, unsigned long long* nnz) {
+    __shared__ unsigned s_cnt[8], s_dns[8], s_nu[8];
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     dense = __reduce_add_sync(0xffffffffu, dense);
+    nonunit = __reduce_add_sync(0xffffffffu, nonunit);
     if ((threadIdx.x & 31) == 0) {
         s_cnt[threadIdx.x >> 5] = cnt;
         s_dns[threadIdx.x >> 5] = dense;
+        s_nu[threadIdx.x >> 5] = nonunit;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = 0, d = 0;
+        unsigned t = 0, d = 0, u = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             t += s_cnt[i];
             d += s_dns[i];
+            u += s_nu[i];
         }
         if (t) atomicAdd(nnz, (unsigned long long)t);
         if (d) atomicAdd(nnz + 2, (unsigned long long)d);
+        if (u) atomicAdd(nnz + 4, (unsigned long long)u);
     }
 }
 
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __res
     const long long nw = (n + 31) >> 5;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0, dns = 0;
+    unsigned cnt = 0, dns = 0, nun = 0;
     for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
         const long long i = wb + lane;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -110,13 +116,17 @@ __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __res
                     out[8 * i + q] = o[q];
                 }
         }
-        unsigned bits = 0;
+        unsigned bits = 0, ones = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) bits |= (o[q] != 0.f ? 1u : 0u) << q;
+        for (int q = 0; q < 8; ++q) {
+            bits |= (o[q] != 0.f ? 1u : 0u) << q;
+            ones |= (o[q] == 1.f ? 1u : 0u) << q;
+        }
         cnt += __popc(bits);
+        nun += __popc(bits & ~ones);
         dns += store_mask_words<8>(bits, wb, mask, nw);
     }
-    add_count(cnt, dns, nnz);
+    add_count(cnt, dns, nun, nnz);
 }
 
 __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n,
@@ -124,10 +134,10 @@ __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __
     const long long nc = (n + 15) >> 4;  // 16-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0, dns = 0;
+    unsigned cnt = 0, dns = 0, nun = 0;
     for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
         const long long i = wb + lane;
-        unsigned bits = 0;
+        unsigned bits = 0, big = 0;
         if (16 * i + 15 < n) {
             const uint4 v = reinterpret_cast<const uint4*>(in)[i];
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -137,18 +147,21 @@ __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __
                 const unsigned b0 = w[k] & 0xffu, b1 = (w[k] >> 8) & 0xffu, b2 = (w[k] >> 16) & 0xffu, b3 = w[k] >> 24;
                 o[k] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
                 bits |= ((b0 != 0 ? 1u : 0u) | (b1 != 0 ? 2u : 0u) | (b2 != 0 ? 4u : 0u) | (b3 != 0 ? 8u : 0u)) << (4 * k);
+                big |= ((b0 > 1 ? 1u : 0u) | (b1 > 1 ? 2u : 0u) | (b2 > 1 ? 4u : 0u) | (b3 > 1 ? 8u : 0u)) << (4 * k);
             }
         } else {
             for (long long j = 16 * i; j < n; ++j) {
                 const unsigned char b = in[j];
                 out[j] = (float)b;
                 bits |= (b != 0 ? 1u : 0u) << (int)(j - 16 * i);
+                big |= (b > 1 ? 1u : 0u) << (int)(j - 16 * i);
             }
         }
         cnt += __popc(bits);
+        nun += __popc(big);
         dns += store_mask_words<16>(bits, wb, mask, (n + 31) >> 5);
     }
-    add_count(cnt, dns, nnz);
+    add_count(cnt, dns, nun, nnz);
 }
 
 __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict__ in, long long n, unsigned long long* nnz,
@@ -156,7 +169,7 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict_
     const long long nq = (n + 3) >> 2;  // 4-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    unsigned cnt = 0, dns = 0;
+    unsigned cnt = 0, dns = 0, nun = 0;
     for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nq; wb += stride) {
         const long long i = wb + lane;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -168,10 +181,12 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict_
             if (4 * i + 2 < n) v.z = in[4 * i + 2];
         }
         const unsigned bits = (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
+        const unsigned ones = (v.x == 1.f ? 1u : 0u) | (v.y == 1.f ? 2u : 0u) | (v.z == 1.f ? 4u : 0u) | (v.w == 1.f ? 8u : 0u);
         cnt += __popc(bits);
+        nun += __popc(bits & ~ones);
         dns += store_mask_words<4>(bits, wb, mask, (n + 31) >> 5);
     }
-    add_count(cnt, dns, nnz);
+    add_count(cnt, dns, nun, nnz);
 }
 
 template <typename T>
@@ -230,9 +245,9 @@ extern "C" int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n,
 
 extern "C" int64_t sn_grid_state_bytes(int64_t n) {
     if (n < 0) return SN_ERR_BAD_ARG;
-    // four counters (count, ticket, dense words, reserved), one mask bit per voxel, 4 padding words (the forward reads
-    // word pairs), rounded to 16 bytes
-    return (32 + 4 * ((n + 31) / 32 + 4) + 15) & ~(int64_t)15;
+    // SN_STATE_WORDS counters, one mask bit per voxel + 4 padding words (the forward reads word pairs), then the list of
+    // tiles the occupancy-driven forward hands to the dense stencil (sn::state_tile_cap(n) 32-bit tile ids); 16-byte multiple
+    return (8 * SN_STATE_WORDS + 4 * (sn::state_mask_words(n) + sn::state_tile_cap(n)) + 15) & ~(int64_t)15;
 }
 
 extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream) {
@@ -242,10 +257,10 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     if (dtype == SN_F32 && x32 && (const void*)x32 != x) return SN_ERR_BAD_ARG;  // float32 grids are used in place
     if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 15)) return SN_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(nnz, 0, 4 * sizeof(unsigned long long), s);  // [0] count, [1] ticket of the tap-gradient tail, [2] dense words
+    cudaError_t e = cudaMemsetAsync(nnz, 0, SN_STATE_WORDS * sizeof(unsigned long long), s);  // the counters (scenenet_b200.h)
     if (e != cudaSuccess) return sn::cuda_rc(e);
     if (n == 0) return SN_OK;
-    unsigned* mask = reinterpret_cast<unsigned*>(nnz + 4);  // occupancy bits follow the four counters (sn_grid_state_bytes)
+    unsigned* mask = reinterpret_cast<unsigned*>(nnz + SN_STATE_WORDS);  // occupancy bits follow the counters
     if (dtype == SN_F64)
         sn::prepare_f64_kernel<<<sn::grid_for(n / 8 + 1, 256), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
     else if (dtype == SN_U8)

@@ -168,7 +168,7 @@ extern "C" int sn_scenenet_g0(const void* pred, int pred_dtype, const void* dpre
 // occupancy (in percent of the voxels) up to which the occupancy-driven kernel is selected: measured break-even
 // at config 2 is ~11 % (dense 101 us flat; occupancy-driven 34 us + 5.5 us per percent, scratch/time_sparse.py)
 static unsigned long long sparse_nnz_max(long long nvox) {
-    static const int pct = getenv("SN_SPARSE_PCT") ? atoi(getenv("SN_SPARSE_PCT")) : 10;
+    static const int pct = SN_ENV("SN_SPARSE_PCT") ? atoi(SN_ENV("SN_SPARSE_PCT")) : 10;
     return (unsigned long long)(nvox / 100 * pct);
 }
 

@@ -89,8 +89,8 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_barrier_init();
-        if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
-        if (nstage == 2 && (int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
+        if ((int)blockIdx.x < g.ntiles) issue(blockIdx.x, 0);
+        if (nstage == 2 && (int)blockIdx.x + G < g.ntiles) issue(blockIdx.x + G, 1);
     }
     __syncthreads();
 
@@ -101,7 +101,7 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         const float* sx = s0 + buf * stage;
         const float* sg = sx + halo_stride;
         if (p.use_tma) {
-            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(nstage == 2 ? (k >> 1) : k) & 1u);
+            mbar_wait(&bar[buf], (uint32_t)(nstage == 2 ? (k >> 1) : k) & 1u);
         } else {
             int b, z0, x0, y0;
             decode_tile(tile, g, b, z0, x0, y0);
@@ -129,7 +129,7 @@ stencil_bwd_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap, 
         if (p.use_tma) {
             __syncthreads();  // every warp is done with this stage -> refill it
             const int next = tile + nstage * G;
-            if (tid == 0 && next < g.ntiles && !(p.dbg & 4)) {
+            if (tid == 0 && next < g.ntiles) {
                 fence_proxy_async();
                 issue(next, buf);
             }
@@ -175,7 +175,7 @@ static BwdPlan plan_bwd(int B, int Z, int X, int Y, int kz, int kx) {
     constexpr int MICRO = kStencilThreads;  // TX * TYT
     BwdPlan pl;
     pl.ncombos = kx * g.nchunks;
-    static const int exp_mode = getenv("SN_BWD_PLAN") ? atoi(getenv("SN_BWD_PLAN")) : 0;  // experiments: 1 = 2 CTAs x 10 warps, single stage
+    static const int exp_mode = SN_ENV("SN_BWD_PLAN") ? atoi(SN_ENV("SN_BWD_PLAN")) : 0;  // experiments: 1 = 2 CTAs x 10 warps, single stage
     const int max_warps = exp_mode == 1 ? 10 : kBwdMaxThreads / 32;
     pl.grid_y = ceil_div(pl.ncombos, max_warps);
     pl.combos_per_cta = ceil_div(pl.ncombos, pl.grid_y);
@@ -209,10 +209,6 @@ static int launch_bwd(BwdParams p, void* ws, int64_t ws_bytes, int* rows_out, cu
     p.TP = pl.TP;
     p.Q = pl.Q;
     p.nstage = p.use_tma ? pl.nstage : 1;
-    {
-        const char* e = getenv("SN_BWD_DBG");
-        p.dbg = e ? atoi(e) : 0;
-    }
     auto kern = stencil_bwd_kernel<KY, TYT, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_rc(e);

@@ -48,12 +48,22 @@ struct FwdParams {
     void* pred;
     int B, Z, X, Y, kz, kx;
     int out_f64, use_tma;
-    int dbg;  // debugging/profiling switches (SN_FWD_DBG): 1 = no stores, 2 = no tanh, 4 = no TMA
     // z-split passes for kernels whose full halo would leave one 4-warp CTA per SM (13^3, 15^3): a pass applies
     // the z-taps [dz0, dz0 + kz) of the full kernel (Kstar already points at tap dz0; plz = full left pad - dz0).
     // pass_mode bit 0: add the partial sum the previous pass left in pred; bit 1: store the raw partial sum
     // (no relu(tanh)) for the next pass.  Partial sums live in pred's own element slots (float -> double is exact).
     int plz, pass_mode;
+    int comp;  // compensated accumulation (set by the launcher for kernels with more than kCompTaps taps)
+    // ABI v4 — tile-list pass: the occupancy-driven forward ran first and left the tiles above its break-even occupancy
+    // in tile_list (state[3] of them); this stencil computes exactly those.  The last CTA to finish the last z-split
+    // pass zeroes state[3] and state[6] again.
+    const int* tile_list;
+    unsigned long long* state;
+    int last_pass;
+    // float64 re-evaluation of sums within rounding distance of zero (exact_sum_f64): unrounded taps of the FULL kernel
+    // (all z-split passes) + sum |tap|, the full kernel's z extent and left pad
+    const double* k64;
+    int full_kz, full_plz;
     // device-side selection against the occupancy-driven kernel (stencil_fwd_sparse.cu): this dense stencil returns
     // at once when nnz != NULL and *nnz <= nnz_max
     const unsigned long long* nnz;
@@ -71,7 +81,6 @@ struct BwdParams {
     int pred_f64, dpred_f64, use_tma;
     int ncombos, combos_per_cta, TP;
     int Q, nstage;  // warps per tap group; TMA pipeline stages
-    int dbg;        // profiling switch (SN_BWD_DBG): 4 = no TMA
     // device-side selection between this dense stencil and the occupancy-driven kernel (stencil_bwd_sparse.cu):
     // the dense kernel returns at once when nnz != NULL and *nnz <= nnz_max
     const unsigned long long* nnz;
@@ -138,6 +147,86 @@ __device__ __forceinline__ double tanh_pos_f64(double s) {
     rc = fma(rc, fma(-d, rc, 1.0), rc);
     rc = fma(rc, fma(-d, rc, 1.0), rc);
     return (1.0 - t) * rc;
+}
+
+// tanh(s) for s > 0 in float64, table-driven (the occupancy-driven forward's epilogue: one call per output voxel, so its
+// instruction count is the kernel's — the polynomial version above was 38 instructions, this one ~24):
+// exp(-2s) = 2^k * 2^(j/64) * e^r with n = rint(-2s * 64/ln2) = 64 k + j, |r| <= ln2/128: degree-4 Taylor (1e-13),
+// 2^(j/64) from a 64-entry table (`tab`: shared memory copy of kExp2Tab — constant memory would serialise the per-lane
+// index); quotient (1 - t)/(1 + t) from the reciprocal seed + two Newton steps.  Absolute error < 1e-12.
+__constant__ double kExp2Tab[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+__device__ __forceinline__ double tanh_pos_f64_tab(double s, const double* __restrict__ tab) {
+    s = fmin(s, 20.0);  // s > 0 (caller); tanh(20) == 1 to the last bit
+    const double x = -2.0 * s;
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);  // + 1.5 * 2^52: the low word is rint(x * 64/ln2)
+    const int n = __double2loint(t);                                  // in [-3694, 0]
+    const double nf = t - 6755399441055744.0;
+    const double r = fma(nf, -0.010830424696249145, x);               // x - n ln2/64
+    double q = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const double u0 = tab[n & 63] * q;
+    const double u = __hiloint2double(__double2hiint(u0) + ((n >> 6) << 20), __double2loint(u0));  // u0 * 2^k, k in [-58, 0]
+    const double d = 1.0 + u;  // in (1, 2]
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));
+    rc = fma(rc, fma(-d, rc, 1.0), rc);
+    rc = fma(rc, fma(-d, rc, 1.0), rc);
+    return (1.0 - u) * rc;
+}
+
+// ---- the sign of sums near zero (ABI v4) ------------------------------------------------------------------------------
+// pred = relu(tanh(s)) has a kink at s = 0 and its derivative jumps from 0 to 1 there: a voxel whose float32 sum has the
+// wrong SIGN changes the whole gradient contribution of that voxel (dL/ds = dL/dpred instead of 0).  Found with the
+// unmodified reference on BASELINE config 2 at its full size (8.4 M voxels): ONE voxel with s_ref = 4.1e-8 came out
+// negative in float32 and moved the 11 parameter gradients by 2.4e-4 relative — 24 x the 1e-5 bar — while every gradient
+// agreed to 2e-7 with the reference's gate (gpurun_out/r2c_diag.log, profiles/r2_notes.md).  So a voxel whose float32
+// sum lies within rounding distance of zero is summed again in float64 with the unrounded taps Kstar64: its sign then
+// agrees with the reference's float64 convolution unless |s_ref| < ~1e-15.  ~6e-5 of the voxels of a config-2 batch.
+struct ExactSum {
+    const float* x;       // [B,1,Z,X,Y] float32 grid
+    const double* k64;    // [T+1]: unrounded taps of the FULL kernel, then sum |tap|; NULL = feature off
+    int Z, X, Y, kz, kx, ky, plz, plx, ply;  // full kernel extents and its left pads
+    float eps_rel;        // |s| < eps_rel * k64[T] is "near zero": 2^-18 for running float32 sums, 2^-21 compensated
+};
+static __device__ __noinline__ double exact_sum_f64(const ExactSum& c, int b, int gz, int gx, int gy) {
+    double s = 0.0;
+    const float* xb = c.x + (size_t)b * c.Z * c.X * c.Y;
+    for (int dz = 0; dz < c.kz; ++dz) {
+        const int z = gz + dz - c.plz;
+        if (z < 0 || z >= c.Z) continue;
+        for (int dx = 0; dx < c.kx; ++dx) {
+            const int xx = gx + dx - c.plx;
+            if (xx < 0 || xx >= c.X) continue;
+            const float* row = xb + ((size_t)z * c.X + xx) * c.Y;
+            const double* kr = c.k64 + (dz * c.kx + dx) * c.ky;
+            for (int dy = 0; dy < c.ky; ++dy) {
+                const int y = gy + dy - c.ply;
+                if (y >= 0 && y < c.Y) {
+                    const float v = __ldg(row + y);
+                    if (v != 0.f) s = fma((double)v, __ldg(kr + dy), s);
+                }
+            }
+        }
+    }
+    return s;
 }
 
 // Tail of the tap-gradient kernels: the CTA that draws the last ticket sums the partial rows of all CTAs in row order

@@ -45,9 +45,11 @@ __device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __r
 // instruction cache level (profiles/r1_notes.md).
 // tanhf, not a float64 tanh: inside this FFMA-bound kernel every float64 variant tried cost +25 % .. +38 % of the
 // kernel (FP64 issue is scarce on B200; see tanh_pos_f64 in stencil_common.cuh, which the occupancy-driven kernel uses).
-static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, size_t idx, int out_f64, int ny,
-                                       bool vec, int dbg, int pass_mode) {
+static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, const ExactSum* ex, float eps,
+                                              int b, int gz, int gx, int gy, int out_f64, bool vec, int pass_mode) {
     float o[4] = {a0, a1, a2, a3};
+    const size_t idx = (((size_t)b * ex->Z + gz) * ex->X + gx) * ex->Y + gy;
+    const int ny = ex->Y - gy;
     if (pass_mode & 1) {  // z-split: add the previous passes' partial sum (stored in this row's own slots)
         if (out_f64) {
             const double* in = reinterpret_cast<const double*>(pred) + idx;
@@ -61,11 +63,15 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
                 if (r < ny) o[r] = in[r] + o[r];
         }
     }
-    if (!(dbg & 2) && !(pass_mode & 2)) {
+    if (!(pass_mode & 2)) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) o[r] = o[r] > 0.f ? tanhf(o[r]) : 0.f;
+        for (int r = 0; r < 4; ++r) {
+            float sv = o[r];
+            // within float32 rounding distance of zero: the sign (the relu gate) is decided in float64 (stencil_common.cuh)
+            if (sv != 0.f && fabsf(sv) < eps && r < ny) sv = (float)exact_sum_f64(*ex, b, gz, gx, gy + r);
+            o[r] = sv > 0.f ? fmaxf(tanhf(sv), 1.401298464e-45f) : 0.f;
+        }
     }
-    if ((dbg & 1) && o[0] != 123.456f) return;
     if (out_f64) {
         double* out = reinterpret_cast<double*>(pred) + idx;
         if (vec) {
@@ -88,12 +94,69 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
     }
 }
 
+// Epilogue of the COMPENSATED kernels (T > kCompTaps taps, BASELINE config 4's 11^3 .. 15^3): the sum arrives as an
+// unevaluated float32 pair (hi, lo).  float64 predictions: the pair and the previous z-split passes' partial sums are
+// combined in float64 (the partial sums live in pred's own float64 slots) and tanh is evaluated in float64 — next to
+// >= 1000 FFMAs per voxel the float64 work is noise; float32 predictions: hi + lo rounded once, tanhf.
+static __device__ __noinline__ void store_row_comp(const float (&hi)[4], const float (&lo)[4], void* pred, const ExactSum* ex, float eps,
+                                                   int b, int gz, int gx, int gy, int out_f64, bool vec, int pass_mode) {
+    const size_t idx = (((size_t)b * ex->Z + gz) * ex->X + gx) * ex->Y + gy;
+    const int ny = ex->Y - gy;
+    if (out_f64) {
+        double* out = reinterpret_cast<double*>(pred) + idx;
+        double o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            o[r] = (double)hi[r] + (double)lo[r];
+            if ((pass_mode & 1) && r < ny) o[r] += out[r];
+            if (!(pass_mode & 2)) {
+                if (o[r] != 0.0 && fabs(o[r]) < (double)eps && r < ny) o[r] = exact_sum_f64(*ex, b, gz, gx, gy + r);
+                o[r] = tanh_pos_f64(o[r]);  // relu inside (negative sums clamp to 0)
+            }
+        }
+        if (vec) {
+            reinterpret_cast<double2*>(out)[0] = make_double2(o[0], o[1]);
+            reinterpret_cast<double2*>(out)[1] = make_double2(o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < ny) out[r] = o[r];
+        }
+    } else {
+        float* out = reinterpret_cast<float*>(pred) + idx;
+        float o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            o[r] = hi[r] + lo[r];
+            if ((pass_mode & 1) && r < ny) o[r] += out[r];
+            if (!(pass_mode & 2)) {
+                if (o[r] != 0.f && fabsf(o[r]) < eps && r < ny) o[r] = (float)exact_sum_f64(*ex, b, gz, gx, gy + r);
+                o[r] = o[r] > 0.f ? fmaxf(tanhf(o[r]), 1.401298464e-45f) : 0.f;
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < ny) out[r] = o[r];
+        }
+    }
+}
+
+// kernels with more taps than this accumulate compensated (COMP): float32 running sums over thousands of taps cost
+// 1.2e-5 .. 1.4e-5 on the worst parameter gradient at 13^3 / 15^3 (CPU emulation scratch/precision_probe3.py: the exact
+// sum rounded once to float32 gives 2e-6 .. 5e-6), above north_star's 1e-5 bar
+constexpr int kCompTaps = 1000;
+
 // Persistent CTAs (4 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a CTA's halo
-// load (one TMA box) is covered by the other CTAs of the SM (optionally a two-stage pipeline with 2 CTAs
-// per SM: tile k+2 in flight while tile k is being computed).  (The first version launched one CTA per tile: all CTAs of a wave waited for
-// their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %.)
-template <int KY, int TYT, int REM>
-__global__ void __launch_bounds__(kStencilThreads, 4)
+// load (one TMA box) is covered by the other CTAs of the SM.  (The first version launched one CTA per tile: all CTAs of
+// a wave waited for their 55 KB halo at the same time — profiles/r1_notes.md — and the FMA pipe idled ~45 %; a two-stage
+// pipeline with 2 CTAs per SM measured 4.5 % slower than this single stage with 4.)
+// COMP: every dx step's partial sum (kz * KY taps, a handful of them non-zero) is added to an unevaluated (hi, lo)
+// float32 pair by an error-free TwoSum: 6 FADDs per accumulator per dx step against kz * KY FFMAs (3.5 % at 13^3).
+template <int KY, int TYT, int REM, bool COMP>
+__global__ void __launch_bounds__(kStencilThreads, COMP ? 2 : 4)
 stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) {
     if (p.nnz && fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // sparse input: the occupancy-driven kernel does the work
     constexpr int C = Geo<KY>::C, CKP = Geo<KY>::CKP;
@@ -101,28 +164,25 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);
     const int halo_floats = g.HZ * g.HX * g.WS;
     const int halo_stride = (halo_floats + 31) & ~31;
-    // single stage + 4 CTAs per SM measured 4.5 % faster than two stages + 2 CTAs per SM (the other CTAs cover
-    // a CTA's halo wait and its tanhf epilogue); dbg 16 selects the two-stage variant
-    const int nbuf = (p.use_tma && (p.dbg & 16)) ? 2 : 1;
     float* sx0 = reinterpret_cast<float*>(smem_raw);
-    float* sk = sx0 + nbuf * halo_stride;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));  // [2]
+    float* sk = sx0 + halo_stride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sk + ((p.kx * g.nchunks * CKP + 31) & ~31));
     const int tid = threadIdx.x;
     const int G = gridDim.x;
 
-    auto issue = [&](int tile, int buf) {  // thread 0 only
+    auto issue = [&](int tile) {  // thread 0 only
         int b, z0, x0, y0;
         decode_tile(tile, g, b, z0, x0, y0);
-        mbar_arrive_expect_tx(&bar[buf], (uint32_t)halo_floats * 4u);
-        tma_load_4d(sx0 + buf * halo_stride, &tmap, &bar[buf], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
+        mbar_arrive_expect_tx(&bar[0], (uint32_t)halo_floats * 4u);
+        tma_load_4d(sx0, &tmap, &bar[0], y0 - g.ply, x0 - g.plx, z0 - g.plz, b);
     };
 
+    // tile-list pass: the tiles the occupancy-driven forward left for this stencil (count written before this launch)
+    const int ntl = p.tile_list ? (int)*reinterpret_cast<volatile unsigned long long*>(p.state + 3) : g.ntiles;
     if (p.use_tma && tid == 0) {
         mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
         fence_barrier_init();
-        if ((int)blockIdx.x < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x, 0);
-        if (nbuf == 2 && (int)blockIdx.x + G < g.ntiles && !(p.dbg & 4)) issue(blockIdx.x + G, 1);
+        if ((int)blockIdx.x < ntl) issue(p.tile_list ? __ldg(p.tile_list + blockIdx.x) : (int)blockIdx.x);
     }
     // taps -> shared once per CTA, re-laid out as [dx][chunk][dzl*KY + dy] (zero padded to CKP)
     for (int i = tid; i < p.kx * g.nchunks * CKP; i += kStencilThreads) sk[i] = 0.f;
@@ -137,15 +197,20 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
     const int tyi = tid % TYT, txi = tid / TYT;
     const int zstride = g.HX * g.WS;
     const bool vec = ((p.Y & 3) == 0);
+    ExactSum ex;
+    ex.x = p.x; ex.k64 = p.k64; ex.Z = p.Z; ex.X = p.X; ex.Y = p.Y; ex.kz = p.full_kz; ex.kx = p.kx; ex.ky = KY;
+    ex.plz = p.full_plz; ex.plx = g.plx; ex.ply = Geo<KY>::PL; ex.eps_rel = 0.f;
+    // |s| below this is "within rounding distance of zero": 2^-18 (running float32 sums) / 2^-21 (compensated) of sum |tap|
+    const float eps = p.k64 ? (float)(__ldg(p.k64 + p.full_kz * p.kx * KY) * (COMP ? 4.76837158203125e-7 : 3.814697265625e-6)) : 0.f;
 
     int k = 0;
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += G, ++k) {
+    for (int ti = blockIdx.x; ti < ntl; ti += G, ++k) {
+        const int tile = p.tile_list ? __ldg(p.tile_list + ti) : ti;
         int b, z0, x0, y0;
         decode_tile(tile, g, b, z0, x0, y0);
-        const int buf = nbuf == 2 ? (k & 1) : 0;
-        const float* sx = sx0 + buf * halo_stride;
+        const float* sx = sx0;
         if (p.use_tma) {
-            if (!(p.dbg & 4)) mbar_wait(&bar[buf], (uint32_t)(nbuf == 2 ? (k >> 1) : k) & 1u);
+            mbar_wait(&bar[0], (uint32_t)k & 1u);
         } else {
             __syncthreads();  // previous tile fully consumed
             load_halo_plain(sx0, p.x, g, p.Z, p.X, p.Y, b, z0, x0, y0, kStencilThreads);
@@ -153,10 +218,14 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
         }
 
         float acc[kRZ][4];
+        float hi[COMP ? kRZ : 1][4], lo[COMP ? kRZ : 1][4];
 #pragma unroll
         for (int i = 0; i < kRZ; ++i)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+            for (int r = 0; r < 4; ++r) {
+                acc[i][r] = 0.f;
+                if constexpr (COMP) { hi[i][r] = 0.f; lo[i][r] = 0.f; }
+            }
 
         // Empty halo -> the tile's sums are exactly zero: skip the tap loop.  Point-cloud grids are clustered (in the
         // reference's data-sample/sample_575.npy 41 of the 64 tiles of the 64^3 grid hold no occupied voxel), and those are
@@ -181,14 +250,28 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
                 const float* skrow = sk + dx * g.nchunks * CKP;
                 for (int ch = 0; ch < nfull; ++ch) fwd_chunk<KY, C>(acc, sxrow + (ch * C) * zstride, zstride, skrow + ch * CKP);
                 if constexpr (REM > 0) fwd_chunk<KY, REM>(acc, sxrow + (nfull * C) * zstride, zstride, skrow + nfull * CKP);
+                if constexpr (COMP) {
+#pragma unroll
+                    for (int i = 0; i < kRZ; ++i)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {  // (hi, lo) += acc, error-free (Knuth TwoSum)
+                            const float a = hi[i][r], c = acc[i][r];
+                            const float s = __fadd_rn(a, c);
+                            const float bb = __fsub_rn(s, a);
+                            const float e = __fadd_rn(__fsub_rn(a, __fsub_rn(s, bb)), __fsub_rn(c, bb));
+                            hi[i][r] = s;
+                            lo[i][r] = __fadd_rn(lo[i][r], e);
+                            acc[i][r] = 0.f;
+                        }
+                }
             }
         }
 
         if (p.use_tma) {
-            __syncthreads();  // every thread is done reading this buffer -> refill it with tile k+2
-            if (tid == 0 && tile + nbuf * G < g.ntiles && !(p.dbg & 4)) {
+            __syncthreads();  // every thread is done reading the buffer -> refill it with the CTA's next tile
+            if (tid == 0 && ti + G < ntl) {
                 fence_proxy_async();
-                issue(tile + nbuf * G, buf);
+                issue(p.tile_list ? __ldg(p.tile_list + ti + G) : ti + G);
             }
         }
 
@@ -198,34 +281,43 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
 #pragma unroll
             for (int zo = 0; zo < kRZ; ++zo) {
                 const int gz = z0 + zo;
-                if (gz < p.Z)
-                    store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy,
-                              p.out_f64, p.Y - gy, vec, p.dbg, p.pass_mode);
+                if (gz < p.Z) {
+                    if constexpr (COMP)
+                        store_row_comp(hi[zo], lo[zo], p.pred, &ex, eps, b, gz, gx, gy, p.out_f64, vec, p.pass_mode);
+                    else
+                        store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, &ex, eps, b, gz, gx, gy, p.out_f64, vec,
+                                  p.pass_mode);
+                }
             }
+        }
+    }
+    if (p.tile_list && p.last_pass) {
+        // the last CTA of the last pass leaves the hand-off counters at zero for the next forward on this state buffer
+        // (every CTA has read state[3] before it gets here)
+        __syncthreads();
+        if (tid == 0 && atomicAdd(p.state + 6, 1ull) == (unsigned long long)(G - 1)) {
+            atomicExch(p.state + 3, 0ull);
+            atomicExch(p.state + 6, 0ull);
         }
     }
 }
 
-template <int KY, int TYT, int REM>
+template <int KY, int TYT, int REM, bool COMP>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
     FwdParams p = p0;
-    {
-        const char* e = getenv("SN_FWD_DBG");
-        p.dbg = e ? atoi(e) : 0;
-    }
     const TileGeo g = make_geo<KY, TYT>(p.B, p.Z, p.X, p.Y, p.kz, p.kx, p.plz);
     const int halo_stride = (g.HZ * g.HX * g.WS + 31) & ~31;
     const int tap_floats = (p.kx * g.nchunks * Geo<KY>::CKP + 31) & ~31;
     CUtensorMap tmap;
     p.use_tma = make_grid_tmap(&tmap, p.x, p.B, p.Z, p.X, p.Y, g.HZ, g.HX, g.WS) ? 1 : 0;
-    size_t smem = (size_t)(2 * halo_stride + tap_floats) * 4 + 32;
-    if (p.use_tma && smem > 227 * 1024) p.use_tma = 0;  // huge halo: single buffer, plain loads
-    if (!p.use_tma || !(p.dbg & 16)) smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
+    const size_t smem = (size_t)(halo_stride + tap_floats) * 4 + 32;
     if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
-    auto kern = stencil_fwd_kernel<KY, TYT, REM>;
+    auto kern = stencil_fwd_kernel<KY, TYT, REM, COMP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    const int per_sm = max(1, min((p.dbg & 16) ? 2 : 4, (int)((227 * 1024) / (smem + 1024))));
+    const int per_sm = max(1, min(COMP ? 2 : 4, (int)((227 * 1024) / (smem + 1024))));
+    // (tile-list pass: the number of listed tiles is only known on the device; a full grid of CTAs, most of which find
+    // nothing to do when few tiles were handed over)
     const int grid = max(1, min(g.ntiles, kNumSMs * per_sm));
     kern<<<grid, kStencilThreads, smem, stream>>>(p, tmap);
     SN_LAUNCH_CHECK();
@@ -236,7 +328,14 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
 template <int KY, int TYT, int REM>
 struct FwdRemDispatch {
     static int run(const FwdParams& p, cudaStream_t s) {
-        if (p.kz % Geo<KY>::C == REM) return launch_fwd<KY, TYT, REM>(p, s);
+        if (p.kz % Geo<KY>::C == REM) {
+            // compensated accumulation for kernels beyond kCompTaps taps; instantiated for the widths such kernels
+            // come in (ky >= 9: config 4's 11^3 / 13^3 / 15^3 and e.g. (13,9,9))
+            if constexpr (KY >= 9) {
+                if (p.comp) return launch_fwd<KY, TYT, REM, true>(p, s);
+            }
+            return launch_fwd<KY, TYT, REM, false>(p, s);
+        }
         return FwdRemDispatch<KY, TYT, REM - 1>::run(p, s);
     }
 };
@@ -261,7 +360,7 @@ static int fwd_passes(const FwdParams& p0, cudaStream_t s) {
     // CTAs) at 58 % / 69 % (profiles/r1_notes.md)
     constexpr size_t kTwoPerSm = (227 * 1024 - 2048) / 2;
     int npass = 1;
-    static const int forced = getenv("SN_FWD_PASSES") ? atoi(getenv("SN_FWD_PASSES")) : 0;
+    static const int forced = SN_ENV("SN_FWD_PASSES") ? atoi(SN_ENV("SN_FWD_PASSES")) : 0;
     if (forced > 0)
         npass = forced < p0.kz ? forced : p0.kz;
     else
@@ -270,11 +369,15 @@ static int fwd_passes(const FwdParams& p0, cudaStream_t s) {
     npass = ceil_div(p0.kz, kzp);
     for (int i = 0; i < npass; ++i) {
         FwdParams p = p0;
+        p.comp = p0.kz * p0.kx * KY > kCompTaps ? 1 : 0;
         const int dz0 = i * kzp;
         p.kz = (p0.kz - dz0) < kzp ? (p0.kz - dz0) : kzp;
         p.Kstar = p0.Kstar + (size_t)dz0 * p0.kx * KY;
         p.plz = pad_left(p0.kz) - dz0;
         p.pass_mode = (i > 0 ? 1 : 0) | (i < npass - 1 ? 2 : 0);
+        p.last_pass = (i == npass - 1 && p0.last_pass) ? 1 : 0;
+        p.full_kz = p0.kz;
+        p.full_plz = pad_left(p0.kz);
         const int rc = FwdRemDispatch<KY, TYT, Geo<KY>::C - 1>::run(p, s);
         if (rc) return rc;
     }

@@ -50,6 +50,11 @@ struct FsParams {
     // outputs pred_qstride elements apart; the non-zero voxels of a tile are listed ONCE for all of them (fwd_occ_kernel)
     int nq;
     long long pred_qstride;
+    // fwd_occ_kernel (ABI v4)
+    unsigned long long* state;  // the grid state buffer's counters ([3] dense tiles, [4] non-unit voxels, [5] tile counter)
+    int* dense_list;            // tiles handed to the dense stencil (NULL: every tile is scattered here)
+    int dense_thresh;           // ... when their halo box holds more non-zero voxels than this
+    const double* k64;          // [nq][T+1] unrounded taps + sum |tap| (NULL: no float64 re-evaluation near zero)
 };
 
 struct FsEntry {
@@ -271,16 +276,29 @@ fwd_sparse_kernel(const FsParams p) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Mask-driven variant (the one that runs when the caller hands over sn_grid_prepare's state buffer).
+// Mask-driven kernel (the one that runs when the caller hands over sn_grid_prepare's state buffer) — third version.
 //
-// ncu of the scanning kernel above at config 2 (profiles/r1_notes.md): 74 M warp instructions, issue slots 79 % busy —
-// bound by instruction issue, and 30 M of them were phase A (every halo voxel is looked at by ~3 tiles: 16-byte
-// loads, bounds tests, four ballots per load).  sn_grid_prepare now leaves one occupancy BIT per voxel next to the
-// count, so phase A of this kernel reads a halo row's 32-column chunks as funnel-shifted mask words (one lane per
-// (x-row, chunk) pair), gets list positions from a warp prefix sum of the popcounts and only touches x for the
-// voxels that are set.  Phase B walks two list entries per 16-byte load with hand-formed shared-memory addresses;
-// phase C's index arithmetic is hoisted out of the tile loop.  Same lists, fixed accumulation order, no atomics.
-constexpr int kFoPairIt = 3;  // (x-row, chunk) pairs per lane: HX * ceil((IY + ky - 1) / 32) <= 96
+// History (profiles/r1_notes.md, profiles/r2_notes.md): the scanning kernel above was bound by instruction issue (74 M warp
+// instructions at config 2, 30 M of them the scan).  v2 read the halo's occupancy BITS instead (41 M instructions, 62 us)
+// and ncu showed where the rest went: ~20 M in the epilogue (a 38-instruction float64 tanh per voxel, scalar loads with
+// 4-way bank conflicts), 6 M in the listing (one warp prefix scan per 32-column chunk, per-row lists), and the scatter
+// itself at 13 scheduler cycles per (voxel, plane) pair because nothing overlapped its LDS -> FFMA -> STS chains.  v3:
+//   A  one CELL = (halo z-row, x-row, 32-column chunk); every thread owns <= kFoMaxCells consecutive cells, reads their
+//      mask words (two per cell, funnel-shifted), and ONE block-wide exclusive scan of the popcounts places every
+//      non-zero voxel of the halo box in a single list ordered by z-row (row starts padded to even positions: phase B
+//      walks 16-byte entry pairs).  Occupancy grids (state[4] == 0: every non-zero is 1) never touch x.
+//   B  warp zo scatters rows zo .. zo+kz-1 into its plane as before; the next entry pair is loaded while the current one
+//      is applied, and a __syncwarp() after every read-modify-write orders it against the next entry's (other lanes
+//      may own the same accumulator: the PTX memory model requires the barrier; measured cost in r2_notes.md).
+//   C  lanes <-> consecutive y (conflict-free scalar LDS, coalesced 8-byte stores), the accumulator is zeroed as it is
+//      read (no separate zeroing pass; halo margins are scratch and never read), tanh by the table-driven float64
+//      evaluation (~24 instructions), sums within rounding distance of zero re-evaluated in float64 (exact_sum_f64).
+//   Tiles are handed out by an atomic counter in the state buffer (a locally dense tile no longer makes its CTA a
+//   straggler), empty tiles are zero-filled with 16-byte stores, and a tile whose halo holds more than `dense_thresh`
+//   non-zeros is appended to the tile list for the dense stencil that follows on the stream (per-TILE kernel choice:
+//   clustered LiDAR grids get the scatter for their sparse tiles and the FFMA stencil for the ground layer).
+constexpr int kFoMaxCells = 6;    // cells per thread: HZ * HX * ceil((IY + ky - 1) / 32) <= 1536
+constexpr int kFoCap = 1536;      // list entries per round (incl. the <= HZ padding entries)
 
 // acc[addr] += v * k for the lanes with ok != 0 (predicated: no branch, the warp stays converged)
 __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) {
@@ -293,42 +311,57 @@ __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) 
         "f"(v), "f"(k), "r"(ok)
         : "memory");
 }
+#ifdef SN_FO_NOSYNC  // measurement only: the v2 behaviour (relies on in-order LDS/STS of a converged warp)
+#define FO_ORDER()
+#else
+#define FO_ORDER() __syncwarp()
+#endif
 
-template <int NI2, bool OUT64, bool MULTI>
-__global__ void __launch_bounds__(kFsThreads, NI2 <= 2 ? 4 : 3)
+template <int NI2, bool OUT64, bool MULTI, int CPT>  // CPT: cells per thread this instantiation holds (3 or kFoMaxCells)
+__global__ void __launch_bounds__(kFsThreads, NI2 == 1 ? 5 : (NI2 == 2 ? 4 : 3))
 fwd_occ_kernel(const FsParams p) {
     const int nq = MULTI ? p.nq : 1;  // compile-time 1 for the single-observer instantiation: its q loop folds away
-    if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // dense or clustered input: stencil_fwd_kernel does the work
+    if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // whole-grid gate (shapes without tile hand-off)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_floats = p.RP * p.AS;
     const int P = p.kx * p.ky, T = p.kz * P;
     float* acc = reinterpret_cast<float*>(smem_raw);
     const int acc_floats = (kRZ * plane_floats + p.kx * p.AS + 31) & ~31;
-    FsEntry* lists = reinterpret_cast<FsEntry*>(acc + acc_floats);  // [HZ][kFsCap]
-    float* sk = reinterpret_cast<float*>(lists + p.HZ * kFsCap);
-    int* cnt = reinterpret_cast<int*>(sk + ((nq * T + 31) & ~31));  // [HZ] non-zeros per halo z-row
+    FsEntry* lists = reinterpret_cast<FsEntry*>(acc + acc_floats);            // [kFoCap + 2]
+    double* tab = reinterpret_cast<double*>(lists + kFoCap + 2);                // [64] 2^(j/64)
+    float* sk = reinterpret_cast<float*>(tab + 64);                             // [nq * T] taps
+    int* gstart = reinterpret_cast<int*>(sk + ((nq * T + 31) & ~31));           // [HZ + 1] list position of a z-row's first voxel
+    int* pstart = gstart + 32;                                                  // [HZ + 1] the same with rows padded to even length
+    int* wtot = pstart + 32;                                                    // [8] non-zeros per warp
+    int* ctl = wtot + 8;                                                        // [2][4]: tile coordinates b, z0, x0, y0 / -1
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = gridDim.x;
+    for (int i = tid; i < acc_floats; i += kFsThreads) acc[i] = 0.f;
     for (int t = tid; t < nq * T; t += kFsThreads) sk[t] = __ldg(p.Kstar + t);
+    if (tid < 64) tab[tid] = kExp2Tab[tid];
 
-    // phase A constants of this lane: its (x-row, 32-column chunk) pair in each iteration
-    // (flat voxel indices fit 32 bits: the launcher only picks this kernel below 2^31 - 2^20 voxels)
+    // ---- phase A constants: this thread's cells
     const int ply = p.pla - p.off;
     const int HW = p.IY + p.ky - 1;
     const int nwc = (HW + 31) >> 5;
-    const int npairs = p.HX * nwc;
-    int pux[kFoPairIt], pc0[kFoPairIt], poff[kFoPairIt], pbase[kFoPairIt];
-#pragma unroll
-    for (int i = 0; i < kFoPairIt; ++i) {
-        const int pr = 32 * i + lane;
-        pux[i] = pr < npairs ? pr / nwc : -1;
-        pc0[i] = pr < npairs ? (pr - pux[i] * nwc) * 32 : 0;
-        poff[i] = pux[i] * p.Y + pc0[i];                                     // voxel offset from the halo row's origin
-        pbase[i] = ((pux[i] + p.kx - 1) * p.AS + pc0[i] + (p.ky - 1)) << 2;  // accumulator byte offset of bit 0
-    }
+    const int cpr = p.HX * nwc;                       // cells per halo z-row
+    const int ncells = p.HZ * cpr;
+    const int cpt = (ncells + kFsThreads - 1) / kFsThreads;  // <= kFoMaxCells (plan)
     const int zstep = p.X * p.Y;
-    // phase B: lane -> plane taps t' = 32 j + lane (t' = dx * ky + dy)
+    int cvox[CPT];       // voxel offset of the cell's first column from the halo box origin
+    unsigned cinf[CPT];  // accumulator byte offset of its bit 0 | chunk << 16 | x-row << 18 | z-row << 24
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = tid * cpt + i;
+        const bool ok = i < cpt && c < ncells;
+        const int zr = ok ? c / cpr : 0, rem = ok ? c - zr * cpr : 0;
+        const int ux = rem / nwc, wc = rem - ux * nwc;
+        cvox[i] = zr * zstep + ux * p.Y + wc * 32;
+        cinf[i] = ok ? ((unsigned)(((ux + p.kx - 1) * p.AS + wc * 32 + (p.ky - 1)) << 2) | ((unsigned)wc << 16) | ((unsigned)ux << 18) |
+                        ((unsigned)zr << 24))
+                     : 0xffffffffu;
+    }
+    // ---- phase B constants: lane -> plane taps t' = 32 j + lane (t' = dx * ky + dy)
     float* accp = acc + warp * plane_floats;  // this warp's output plane (zo = warp)
     uint32_t accl[NI2];  // shared-memory byte address of this lane's accumulator for an entry with base 0
     int okp[NI2];
@@ -339,206 +372,262 @@ fwd_occ_kernel(const FsParams p) {
         const int tq = okp[j] ? tp : 0;
         accl[j] = smem_u32(accp) - 4u * (uint32_t)((tq / p.ky) * p.AS + (tq % p.ky));
     }
-    const uint32_t lists_w = smem_u32(lists + warp * kFsCap);  // list of halo z-row `warp` (dz = 0)
+    const uint32_t lists_u = smem_u32(lists);
     const float* skl = sk + lane;
-    // phase C: lane -> four 4-voxel groups of the 8 x IX x IY tile's plane (IX * IY == 512)
-    const int lg_gy = p.IY == 64 ? 4 : 3;  // 4-voxel groups per plane row: IY / 4 = 16 or 8
     const bool vec = (p.Y & 3) == 0;
+    const bool binary = p.state ? (p.state[4] == 0ull) : false;  // occupancy grid: every listed value is 1
+    float eps = 0.f;
+    ExactSum ex;
+    ex.x = p.x; ex.k64 = p.k64; ex.Z = p.Z; ex.X = p.X; ex.Y = p.Y; ex.kz = p.kz; ex.kx = p.kx; ex.ky = p.ky;
+    ex.plz = p.plz; ex.plx = p.plx; ex.ply = ply; ex.eps_rel = 0.f;
+    if (p.k64) eps = (float)(__ldg(p.k64 + T) * 3.814697265625e-6);  // 2^-18 * sum |tap| (observer 0; MULTI: per q below)
+
+    // ---- tile hand-out: an atomic counter in the state buffer (static stride without one); thread 0 decodes a tile's
+    // coordinates one tile ahead into ctl[slot]
+    unsigned long long* tctr = p.state ? p.state + 5 : nullptr;
+    const int G = gridDim.x;
+    int static_next = blockIdx.x;
+    auto fetch = [&](int slot) {  // thread 0 only
+        int t;
+        if (tctr) {
+            t = (int)atomicAdd(tctr, 1ull);
+            if (t >= p.ntiles) {
+                if (t == p.ntiles + G - 1) atomicExch(tctr, 0ull);  // the last draw of the launch: ready for the next one
+                t = -1;
+            }
+        } else {
+            t = static_next < p.ntiles ? static_next : -1;
+            static_next += G;
+        }
+        int* c = ctl + 4 * slot;
+        if (t < 0) { c[0] = -1; c[1] = c[2] = c[3] = 0; return; }
+        const int ty = t % p.tiles_y; int r = t / p.tiles_y;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int tz = r % p.tiles_z;
+        c[0] = r / p.tiles_z; c[1] = tz * kRZ; c[2] = tx * p.IX; c[3] = ty * p.IY;
+    };
+    if (tid == 0) fetch(0);
     __syncthreads();
 
-    // tile coordinates advance by the (decoded) grid stride with carries: no divisions inside the tile loop
-    int tc[4], ts[4];  // ty, tx, tz, b of the current tile / of the stride G
-    {
-        int t = blockIdx.x, g = G;
-        tc[0] = t % p.tiles_y; t /= p.tiles_y; ts[0] = g % p.tiles_y; g /= p.tiles_y;
-        tc[1] = t % p.tiles_x; t /= p.tiles_x; ts[1] = g % p.tiles_x; g /= p.tiles_x;
-        tc[2] = t % p.tiles_z; tc[3] = t / p.tiles_z; ts[2] = g % p.tiles_z; ts[3] = g / p.tiles_z;
-    }
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += G) {
-        const int b = tc[3], z0 = tc[2] * kRZ, x0 = tc[1] * p.IX, y0 = tc[0] * p.IY;
-        {
-            tc[0] += ts[0];
-            int cy = tc[0] >= p.tiles_y ? 1 : 0;
-            tc[0] -= cy ? p.tiles_y : 0;
-            tc[1] += ts[1] + cy;
-            cy = tc[1] >= p.tiles_x ? 1 : 0;
-            tc[1] -= cy ? p.tiles_x : 0;
-            tc[2] += ts[2] + cy;
-            cy = tc[2] >= p.tiles_z ? 1 : 0;
-            tc[2] -= cy ? p.tiles_z : 0;
-            tc[3] += ts[3] + cy;
-        }
-        // live halo columns of this tile (gy = y0 - ply + c inside [0, Y)) and live x-rows, per pair of this lane
-        unsigned vm[kFoPairIt];
-        {
-            const int c_lo = max(0, ply - y0), c_hi = min(HW, p.Y - y0 + ply);
+    for (int it = 0;; ++it) {
+        const int* c = ctl + 4 * (it & 1);
+        const int b = c[0], z0 = c[1], x0 = c[2], y0 = c[3];
+        if (b < 0) break;
+        if (tid == 0) fetch((it + 1) & 1);  // visible after this tile's first barrier; read after its last one
+
+        // ---- A1: occupancy words of this thread's cells
+        const int c_lo = max(0, ply - y0), c_hi = min(HW, p.Y - y0 + ply);  // live halo columns [c_lo, c_hi)
+        const int org = ((b * p.Z + (z0 - p.plz)) * p.X + (x0 - p.plx)) * p.Y + (y0 - ply);  // flat index of the box origin (may be < 0)
+        unsigned m[CPT];
+        int mine = 0;
 #pragma unroll
-            for (int i = 0; i < kFoPairIt; ++i) {
-                const int gx = x0 - p.plx + pux[i];
-                const int a = min(max(c_lo - pc0[i], 0), 32), e = min(max(c_hi - pc0[i], 0), 32);
-                vm[i] = (pux[i] >= 0 && gx >= 0 && gx < p.X && e > a) ? ((0xffffffffu >> (32 - (e - a))) << a) : 0u;
+        for (int i = 0; i < CPT; ++i) {
+            m[i] = 0u;
+            if (i < cpt && cinf[i] != 0xffffffffu) {
+                const int wc = (cinf[i] >> 16) & 3, ux = (cinf[i] >> 18) & 63, zr = cinf[i] >> 24;
+                const int gz = z0 - p.plz + zr, gx = x0 - p.plx + ux;
+                const int a = min(max(c_lo - wc * 32, 0), 32), e = min(max(c_hi - wc * 32, 0), 32);
+                if (gz >= 0 && gz < p.Z && gx >= 0 && gx < p.X && e > a) {
+                    const int bit0 = org + cvox[i];
+                    const int wi = bit0 >> 5;  // floor
+                    const unsigned w0 = (unsigned)wi < (unsigned)p.nw ? __ldg(p.mask + wi) : 0u;
+                    const unsigned w1 = (unsigned)(wi + 1) < (unsigned)p.nw ? __ldg(p.mask + wi + 1) : 0u;
+                    m[i] = __funnelshift_r(w0, w1, (unsigned)bit0 & 31u) & ((0xffffffffu >> (32 - (e - a))) << a);
+                }
             }
+            mine += __popc(m[i]);
         }
-        // flat index of the halo box origin (z-row 0, x-row 0, column 0); may be negative at the grid's first rows
-        const int org = ((b * p.Z + (z0 - p.plz)) * p.X + (x0 - p.plx)) * p.Y + (y0 - ply);
-        // One pass per observer q (nq == 1 outside SCENENetQuantile).  The lists of round 0 serve every q; only a tile
-        // with an overflowing row (more than kFsCap non-zeros: further rounds rewrite the lists) lists again for q > 0.
-        bool multi_round = false;
-        for (int q = 0; q < nq; ++q) {
-        if (q > 0 && multi_round) __syncthreads();  // every warp is done reading the last round's lists of q - 1
-        {
-            float4* a4 = reinterpret_cast<float4*>(accp);
-            for (int i = lane; i < (plane_floats >> 2); i += 32) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- A2: block-wide exclusive scan of the per-thread counts
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-        int lo = 0;
-        while (true) {
-            int more = 0;
-            if (q == 0 || multi_round) {
-            // ---- A: list the non-zero voxels [lo, lo + cap) of every halo z-row from the occupancy bits
-            bool my_more = false;
-            for (int zr = warp; zr < p.HZ; zr += kFsWarps) {
-                FsEntry* lst = lists + zr * kFsCap;
-                const int gz = z0 - p.plz + zr;
-                const bool z_ok = gz >= 0 && gz < p.Z;
-                int n = 0;
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();  // (1)
+        int pre = incl - mine, total = 0;
 #pragma unroll
-                for (int i = 0; i < kFoPairIt; ++i) {
-                    if (32 * i >= npairs) break;  // warp-uniform
-                    unsigned m = 0u;
-                    const int bit0 = org + zr * zstep + poff[i];
-                    if (z_ok && vm[i]) {
-                        const int wi = bit0 >> 5;  // floor
-                        const unsigned w0 = (unsigned)wi < (unsigned)p.nw ? __ldg(p.mask + wi) : 0u;
-                        const unsigned w1 = (unsigned)(wi + 1) < (unsigned)p.nw ? __ldg(p.mask + wi + 1) : 0u;
-                        m = __funnelshift_r(w0, w1, (unsigned)bit0 & 31u) & vm[i];
-                    }
-                    const int c = __popc(m);
-                    int incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    int pos = n + incl - c - lo;
-                    while (m) {
-                        const int bp = __ffs(m) - 1;
-                        m &= m - 1u;
-                        if (pos >= 0 && pos < kFsCap) {
-                            FsEntry en;
-                            en.val = __ldg(p.x + (bit0 + bp));
-                            en.base = pbase[i] + (bp << 2);  // byte offset inside the plane
-                            lst[pos] = en;
+        for (int w = 0; w < kFsWarps; ++w) {
+            const int v = wtot[w];
+            pre += w < warp ? v : 0;
+            total += v;
+        }
+        if (total == 0) {
+            // empty halo: every sum of the tile is exactly zero (41 of the 64 tiles of the reference's sample_575 grid)
+            for (int q = 0; q < nq; ++q) {
+                const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + z0) * p.X + x0) * p.Y + y0;
+                for (int g = tid; g < kRZ * p.IX * (p.IY >> 2); g += kFsThreads) {
+                    const int yo = (g % (p.IY >> 2)) << 2, r = g / (p.IY >> 2), xo = r % p.IX, zo = r / p.IX;
+                    if (z0 + zo >= p.Z || x0 + xo >= p.X || y0 + yo >= p.Y) continue;
+                    const size_t idx = idx0 + ((size_t)zo * p.X + xo) * p.Y + yo;
+                    const int ny = p.Y - (y0 + yo);
+                    if constexpr (OUT64) {
+                        double* out = reinterpret_cast<double*>(p.pred) + idx;
+                        if (vec) {
+                            reinterpret_cast<double2*>(out)[0] = make_double2(0.0, 0.0);
+                            reinterpret_cast<double2*>(out)[1] = make_double2(0.0, 0.0);
+                        } else {
+                            for (int r2 = 0; r2 < 4 && r2 < ny; ++r2) out[r2] = 0.0;
                         }
-                        ++pos;
-                    }
-                    n += total;
-                }
-                if (lane == 0) {
-                    cnt[zr] = n;
-                    // phase B walks the list two entries at a time: an odd list gets a no-op entry (value 0 at the
-                    // accumulators of halo voxel (0, 0): inside this warp's own plane for every tap)
-                    const int nl = n - lo;
-                    if (nl > 0 && nl < kFsCap && (nl & 1)) {
-                        FsEntry en;
-                        en.val = 0.f;
-                        en.base = ((p.kx - 1) * p.AS + (p.ky - 1)) << 2;
-                        lst[nl] = en;
+                    } else {
+                        float* out = reinterpret_cast<float*>(p.pred) + idx;
+                        if (vec) {
+                            *reinterpret_cast<float4*>(out) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            for (int r2 = 0; r2 < 4 && r2 < ny; ++r2) out[r2] = 0.f;
+                        }
                     }
                 }
-                my_more |= n > lo + kFsCap;
             }
-            more = __syncthreads_or(my_more ? 1 : 0);
-            if (lo == 0 && more) multi_round = true;
+            __syncthreads();  // wtot / ctl are rewritten by the next tile
+            continue;
+        }
+        if (p.dense_list && total > p.dense_thresh) {
+            // locally dense tile: the dense stencil behind us on the stream computes it (per-tile kernel choice)
+            if (tid == 0) {
+                const int tile = ((b * p.tiles_z + z0 / kRZ) * p.tiles_x + x0 / p.IX) * p.tiles_y + y0 / p.IY;
+                const unsigned long long slot = atomicAdd(p.state + 3, 1ull);
+                p.dense_list[slot] = tile;
             }
-            // ---- B: warp zo adds slice dz of the taps at every listed voxel of row zo + dz
-            for (int dz = 0; dz < p.kz; ++dz) {
-                int n = cnt[warp + dz] - lo;
-                n = n < 0 ? 0 : (n > kFsCap ? kFsCap : n);
-                if (n == 0) continue;
-                float kk[NI2];
+            __syncthreads();
+            continue;
+        }
+        // ---- A3: row starts.  Cells are numbered z-row major, so the list is ordered by z-row.
+        {
+            int run = pre;
 #pragma unroll
-                for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[q * T + dz * P + 32 * j] : 0.f;
-                // two list entries per 16-byte broadcast load; shared-memory addresses are formed by hand (the generic
-                // C++ form cost 12 instructions per entry, this one 5) and the read-modify-write is predicated, not
-                // branched, so the warp stays converged: its LDS / STS are executed in program order, which is what
-                // makes an entry see the sums its predecessor stored from OTHER lanes
-                __syncwarp();
-                uint32_t la = lists_w + (uint32_t)dz * (kFsCap * 8u);
-                const uint32_t lend = la + (((uint32_t)n + 1u) >> 1) * 16u;
-#pragma unroll 1
-                for (; la != lend; la += 16u) {
+            for (int i = 0; i < CPT; ++i) {
+                if (i < cpt && cinf[i] != 0xffffffffu && (cinf[i] & 0x00ff0000u) == 0u) gstart[cinf[i] >> 24] = run;  // chunk 0 of x-row 0
+                run += __popc(m[i]);
+            }
+            if (tid == 0) gstart[p.HZ] = total;
+        }
+        __syncthreads();  // (2)
+        if (warp == 0) {
+            const int r = lane < p.HZ ? lane : p.HZ;
+            const int g0 = gstart[r], g1 = lane < p.HZ ? gstart[r + 1] : g0;
+            const unsigned odd = __ballot_sync(0xffffffffu, (g1 - g0) & 1);
+            if (lane <= p.HZ) pstart[lane] = g0 + __popc(odd & ((1u << lane) - 1u));
+        }
+        __syncthreads();  // (3)
+        const int total_p = pstart[p.HZ];  // padded length of the list
+
+        bool multi_round = total_p > kFoCap;
+        for (int q = 0; q < nq; ++q) {
+            if (MULTI && p.k64) eps = (float)(__ldg(p.k64 + (size_t)q * (T + 1) + T) * 3.814697265625e-6);
+            for (int lo = 0; lo < total_p; lo += kFoCap) {
+                if (q == 0 || multi_round) {
+                    if (lo > 0 || q > 0) __syncthreads();  // every warp is done with the previous round's list
+                    // ---- A4: write the entries of the window [lo, lo + kFoCap)
+                    int run = pre;
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        unsigned mm = m[i];
+                        if (mm) {
+                            const int zr = cinf[i] >> 24;
+                            int pos = pstart[zr] + (run - gstart[zr]) - lo;
+                            const int bit0 = org + cvox[i];
+                            const int base = (int)(cinf[i] & 0xffffu);
+                            run += __popc(mm);
+                            while (mm) {
+                                const int bp = __ffs(mm) - 1;
+                                mm &= mm - 1u;
+                                if (pos >= 0 && pos < kFoCap) {
+                                    FsEntry en;
+                                    en.val = binary ? 1.f : __ldg(p.x + (bit0 + bp));
+                                    en.base = base + (bp << 2);  // byte offset inside the plane
+                                    lists[pos] = en;
+                                }
+                                ++pos;
+                            }
+                        }
+                    }
+                    if (warp == 0 && lane < p.HZ) {
+                        // odd rows end with a no-op entry (value 0 at the accumulators of halo voxel (0, 0): inside the
+                        // warp's own plane for every tap)
+                        const int n = gstart[lane + 1] - gstart[lane];
+                        const int pos = pstart[lane] + n - lo;
+                        if ((n & 1) && pos >= 0 && pos < kFoCap) {
+                            FsEntry en;
+                            en.val = 0.f;
+                            en.base = ((p.kx - 1) * p.AS + (p.ky - 1)) << 2;
+                            lists[pos] = en;
+                        }
+                    }
+                    __syncthreads();  // (4) the list is complete
+                }
+                // ---- B: warp zo adds slice dz of the taps at every listed voxel of z-row zo + dz
+                for (int dz = 0; dz < p.kz; ++dz) {
+                    int s0 = pstart[warp + dz] - lo, s1 = pstart[warp + dz + 1] - lo;  // even positions
+                    s0 = s0 < 0 ? 0 : s0;
+                    s1 = s1 > kFoCap ? kFoCap : s1;
+                    if (s0 >= s1) continue;
+                    float kk[NI2];
+#pragma unroll
+                    for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[q * T + dz * P + 32 * j] : 0.f;
+                    uint32_t la = lists_u + (uint32_t)s0 * 8u;
+                    const uint32_t lend = lists_u + (uint32_t)s1 * 8u;
                     float v0, v1;
                     uint32_t b0, b1;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=r"(b0), "=f"(v1), "=r"(b1) : "r"(la) : "memory");
-#pragma unroll
-                    for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b0, v0, kk[j], okp[j]);
-#pragma unroll
-                    for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b1, v1, kk[j], okp[j]);
-                }
-            }
-            if (!more) break;
-            __syncthreads();  // the lists are rewritten by the next round
-            lo += kFsCap;
-        }
-        // ---- C: epilogue of this warp's plane (lane -> 4 consecutive y)
-        {
-            const int gz = z0 + warp;
-            const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) {
-                const int g = lane + 32 * i;
-                const int xo = g >> lg_gy, yo = (g & ((1 << lg_gy) - 1)) << 2;
-                const int gx = x0 + xo, gy = y0 + yo;
-                if (gz >= p.Z || gx >= p.X || gy >= p.Y) continue;
-                const float* a = accp + (xo + p.kx - 1) * p.AS + yo + (p.ky - 1);
-                const size_t idx = idx0 + (size_t)xo * p.Y + yo;
-                const int ny = p.Y - gy;
-                if constexpr (OUT64) {  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
-                    double od[4] = {0.0, 0.0, 0.0, 0.0};
-                    const float s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3];
-                    // the four evaluations are branch-free and interleave; a warp whose 128 sums are all <= 0 (empty
-                    // regions of a scene) skips them
-                    if (__any_sync(__activemask(), fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > 0.f)) {
-                        od[0] = tanh_pos_f64((double)s0);  // relu inside: negative sums clamp to 0
-                        od[1] = tanh_pos_f64((double)s1);
-                        od[2] = tanh_pos_f64((double)s2);
-                        od[3] = tanh_pos_f64((double)s3);
-                    }
-                    double* out = reinterpret_cast<double*>(p.pred) + idx;
-                    if (vec) {
-                        reinterpret_cast<double2*>(out)[0] = make_double2(od[0], od[1]);
-                        reinterpret_cast<double2*>(out)[1] = make_double2(od[2], od[3]);
-                    } else {
+                    while (true) {
+                        la += 16u;
+                        float n0, n1;
+                        uint32_t c0, c1;  // the next pair (the list has two entries of slack behind its last one)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(n0), "=r"(c0), "=f"(n1), "=r"(c1) : "r"(la) : "memory");
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (r < ny) out[r] = od[r];
-                    }
-                } else {
-                    float o[4];
+                        for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b0, v0, kk[j], okp[j]);
+                        FO_ORDER();
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float s = a[r];
-                        o[r] = s > 0.f ? tanhf(s) : 0.f;
-                    }
-                    float* out = reinterpret_cast<float*>(p.pred) + idx;
-                    if (vec) {
-                        *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (r < ny) out[r] = o[r];
+                        for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b1, v1, kk[j], okp[j]);
+                        FO_ORDER();
+                        if (la == lend) break;
+                        v0 = n0; b0 = c0; v1 = n1; b1 = c1;
                     }
                 }
             }
-        }
+            // ---- C: epilogue of this warp's plane: lanes <-> consecutive y; the accumulators are zeroed as they are read
+            __syncwarp();
+            {
+                const int gz = z0 + warp;
+                const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
+                const int nyh = p.IY >> 5;  // 32-column chunks per output row
+                float* arow = accp + (p.kx - 1) * p.AS + (p.ky - 1) + lane;
+#pragma unroll 1
+                for (int r = 0; r < p.IX * nyh; ++r) {
+                    const int xo = nyh == 2 ? (r >> 1) : r, yo = nyh == 2 ? ((r & 1) << 5) + lane : lane;
+                    float* a = arow + xo * p.AS + (yo - lane);
+                    const float sf = *a;
+                    *a = 0.f;
+                    const int gx = x0 + xo, gy = y0 + yo;
+                    if (gz >= p.Z || gx >= p.X || gy >= p.Y) continue;
+                    const size_t idx = idx0 + (size_t)xo * p.Y + yo;
+                    double sd = (double)sf;
+                    if (sf != 0.f && fabsf(sf) < eps) {  // within float32 rounding distance of zero: the sign decides the gate
+                        ex.k64 = p.k64 + (MULTI ? (size_t)q * (T + 1) : 0);
+                        sd = exact_sum_f64(ex, b, gz, gx, gy);
+                    }
+                    if constexpr (OUT64) {
+                        double o = 0.0;
+                        if (sd > 0.0) o = tanh_pos_f64_tab(sd, tab);
+                        reinterpret_cast<double*>(p.pred)[idx] = o;
+                    } else {
+                        const float s32 = (float)sd;
+                        reinterpret_cast<float*>(p.pred)[idx] = sd > 0.0 ? fmaxf(tanhf(s32), 1.401298464e-45f) : 0.f;
+                    }
+                }
+            }
+            __syncwarp();  // the zeroed accumulators are visible to every lane before the next observer's scatter
         }  // q
-        __syncthreads();  // lists and counts are rewritten by the next tile
+        __syncthreads();  // the list, the row tables and ctl are rewritten by the next tile
     }
 }
 
 // geometry; false when the kernel does not cover the shape (caller uses the dense stencil)
-static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, FsParams& p, size_t& smem, int& ni2, int nq = 1) {
+static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, FsParams& p, size_t& smem, int& ni2, int nq = 1,
+                            size_t* smem_occ = nullptr) {
     p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx; p.ky = ky;
     const int P = kx * ky;
     ni2 = ceil_div(P, 32);
@@ -556,7 +645,7 @@ static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, 
     p.RP = p.HX;
     const int as_min = p.IY + ky - 1;
     p.AS = as_min + (((ky - as_min) % 32) + 32) % 32;  // = ky (mod 32): conflict-free tap addresses
-    // zeroing uses 16-byte stores: the plane size must be a multiple of 4 floats
+    // (the scanning kernel zeroes planes with 16-byte stores: the plane size must be a multiple of 4 floats)
     while ((p.RP * p.AS) & 3) ++p.RP;
     p.tiles_z = ceil_div(Z, kRZ);
     p.tiles_x = ceil_div(X, p.IX);
@@ -571,7 +660,16 @@ static bool plan_fwd_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, 
     const size_t cntb = (size_t)((p.HZ + 1) & ~1) * 4;
     const size_t scanb = (size_t)ceil_div(p.HX * p.WS / 4, 32) * 32 * 16;
     smem = accb + lst + scanb + taps + cntb + 16;
+    if (smem_occ) *smem_occ = accb + (size_t)(kFoCap + 2) * sizeof(FsEntry) + 64 * 8 + taps + (32 + 32 + 8 + 8) * 4 + 16;
     return smem <= 227 * 1024;
+}
+
+// the mask-driven kernel: occupancy bits, at most kFoMaxCells cells per thread, field widths of the packed cell word
+// (2-bit chunk, 6-bit x-row, z-rows / row tables up to 31) and 32-bit flat voxel indices (incl. the halo overshoot)
+static bool occ_kernel_covers(const FsParams& p) {
+    const int nwc = (p.IY + p.ky - 1 + 31) >> 5;
+    return p.mask && p.HZ <= 31 && p.HX <= 63 && nwc <= 3 && p.HZ * p.HX * nwc <= kFoMaxCells * kFsThreads && p.IX * p.IY == 512 &&
+           (size_t)p.RP * p.AS * 4 < 65536 && (long long)p.B * p.Z * p.X * p.Y < (1ll << 31) - (1ll << 20);
 }
 
 bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky) {
@@ -581,49 +679,80 @@ bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky) {
     return plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2);
 }
 
+// true when the mask-driven kernel can hand locally dense tiles of this shape to the dense stencil (same tiling:
+// 8 x (512 / IY) x IY output tiles, and the state buffer's tile list holds every tile)
+bool fwd_tile_handoff_supported(int B, int Z, int X, int Y, int kz, int kx, int ky) {
+    FsParams p{};
+    size_t smem;
+    int ni2;
+    if (!plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2)) return false;
+    p.mask = reinterpret_cast<const unsigned*>(&p);  // any non-null value: the geometry test only
+    return occ_kernel_covers(p) && (long long)p.ntiles <= state_tile_cap((long long)B * Z * X * Y);
+}
+
 template <int NI2>
-static int launch_fs(FsParams& p, size_t smem, cudaStream_t stream) {
-    // the mask-driven kernel needs the occupancy bits, at most kFoPairIt * 32 (x-row, chunk) pairs per halo z-row and
-    // 32-bit flat voxel indices (incl. the halo overshoot)
-    const bool occ = p.mask && p.HX * ((p.IY + p.ky - 1 + 31) >> 5) <= kFoPairIt * 32 && p.IX * p.IY == 512 &&
-                     (long long)p.B * p.Z * p.X * p.Y < (1ll << 31) - (1ll << 20);
+static int launch_fs(FsParams& p, size_t smem, size_t smem_occ, cudaStream_t stream) {
+    const bool occ = occ_kernel_covers(p);
     if (p.nq > 1 && !occ) return SN_ERR_UNSUPPORTED;  // only the mask-driven kernel shares its lists between observers
+    if (!occ) { p.dense_list = nullptr; p.state = nullptr; }
+    const int nwc = (p.IY + p.ky - 1 + 31) >> 5;
+    const bool small = ceil_div(p.HZ * p.HX * nwc, kFsThreads) <= 3;  // e.g. (9,5,5): 16 x 12 x 3 cells = 2.25 per thread
     auto kern = !occ ? fwd_sparse_kernel<NI2>
-                : p.nq > 1 ? (p.out_f64 ? fwd_occ_kernel<NI2, true, true> : fwd_occ_kernel<NI2, false, true>)
-                           : (p.out_f64 ? fwd_occ_kernel<NI2, true, false> : fwd_occ_kernel<NI2, false, false>);
+                : p.nq > 1 ? (p.out_f64 ? (small ? fwd_occ_kernel<NI2, true, true, 3> : fwd_occ_kernel<NI2, true, true, kFoMaxCells>)
+                                        : (small ? fwd_occ_kernel<NI2, false, true, 3> : fwd_occ_kernel<NI2, false, true, kFoMaxCells>))
+                           : (p.out_f64 ? (small ? fwd_occ_kernel<NI2, true, false, 3> : fwd_occ_kernel<NI2, true, false, kFoMaxCells>)
+                                        : (small ? fwd_occ_kernel<NI2, false, false, 3> : fwd_occ_kernel<NI2, false, false, kFoMaxCells>));
+    if (occ) smem = smem_occ;
+    if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
+    const int cap_sm = occ ? (NI2 == 1 ? 5 : (NI2 == 2 ? 4 : 3)) : 4;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > cap_sm ? cap_sm : per_sm);
     const int grid = max(1, min(p.ntiles, kNumSMs * per_sm));
     kern<<<grid, kFsThreads, smem, stream>>>(p);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
 
-int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, const unsigned long long* nnz,
-                      unsigned long long nnz_max, unsigned long long dw_max, const unsigned* occ_mask, int B, int Z, int X, int Y,
-                      int kz, int kx, int ky, int nq, cudaStream_t stream) {
+// state: the grid state buffer (NULL: scanning kernel, no mask); gate: whole-grid selection against the dense stencil
+// (NULL: run); handoff: append tiles above the break-even occupancy to the state buffer's tile list instead of
+// scattering them (the caller enqueues the dense stencil's tile-list pass behind this launch)
+int fwd_sparse_launch(const float* x, const float* Kstar, const double* Kstar64, void* pred, int out_f64, unsigned long long* state,
+                      const unsigned long long* gate, unsigned long long nnz_max, unsigned long long dw_max, bool handoff,
+                      int B, int Z, int X, int Y, int kz, int kx, int ky, int nq, cudaStream_t stream) {
     FsParams p{};
-    size_t smem;
+    size_t smem, smem_occ;
     int ni2;
-    if (nq < 1 || !plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2, nq)) return SN_ERR_UNSUPPORTED;
+    if (nq < 1 || !plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2, nq, &smem_occ)) return SN_ERR_UNSUPPORTED;
     p.nq = nq;
     p.pred_qstride = (long long)B * Z * X * Y;
-    p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = nnz; p.nnz_max = nnz_max; p.dw_max = dw_max;
-    p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64 (tanh_pos_f64)
+    p.x = x; p.Kstar = Kstar; p.k64 = Kstar64; p.pred = pred; p.out_f64 = out_f64; p.nnz = gate; p.nnz_max = nnz_max; p.dw_max = dw_max;
+    p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64
     {
-        static const bool no_mask = getenv("SN_FWD_NO_MASK") != nullptr;  // measurement: force the scanning kernel
-        p.mask = no_mask ? nullptr : occ_mask;
-        const long long nw = ((long long)B * Z * X * Y + 31) >> 5;
+        static const bool no_mask = SN_ENV("SN_FWD_NO_MASK") != nullptr;  // measurement: force the scanning kernel
+        const long long nvox = (long long)B * Z * X * Y;
+        p.state = no_mask ? nullptr : state;
+        p.mask = p.state ? reinterpret_cast<const unsigned*>(p.state + SN_STATE_WORDS) : nullptr;
+        const long long nw = (nvox + 31) >> 5;
         p.nw = nw < (1ll << 30) ? (int)nw : 0;
+        p.dense_list = nullptr;
+        if (p.state && handoff && (long long)p.ntiles <= state_tile_cap(nvox)) {
+            p.dense_list = reinterpret_cast<int*>(const_cast<unsigned*>(p.mask) + state_mask_words(nvox));
+            // break-even of the scatter against the dense stencil, per tile: the scatter costs ~20 scheduler cycles per
+            // (non-zero voxel of the halo box, output plane) pair, the stencil kz * kx * ky / 32 FFMA issue slots per
+            // output voxel; measured crossing at ~10 % occupancy of the box for (9,5,5) (profiles/r2_notes.md)
+            static const double forced = SN_ENV("SN_FWD_TILE_PCT") ? atof(SN_ENV("SN_FWD_TILE_PCT")) : -1.0;
+            const double pct = forced >= 0.0 ? forced : 10.0;
+            p.dense_thresh = (int)((double)p.HZ * p.HX * (p.IY + ky - 1) * pct / 100.0);
+        }
     }
     if ((uintptr_t)x & 15) return SN_ERR_ALIGN;
     switch (ni2) {
-        case 1: return launch_fs<1>(p, smem, stream);
-        case 2: return launch_fs<2>(p, smem, stream);
-        case 3: return launch_fs<3>(p, smem, stream);
-        default: return launch_fs<4>(p, smem, stream);
+        case 1: return launch_fs<1>(p, smem, smem_occ, stream);
+        case 2: return launch_fs<2>(p, smem, smem_occ, stream);
+        case 3: return launch_fs<3>(p, smem, smem_occ, stream);
+        default: return launch_fs<4>(p, smem, smem_occ, stream);
     }
 }
 

@@ -147,7 +147,7 @@ __device__ float lambda_eff_of(const SynthArgs& a, int g) {
 // =====================================================================================
 __global__ void __launch_bounds__(kSynthThreads * kSynthGroups, 1)
 synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restrict__ lambda_eff,
-                 float* __restrict__ Kstar, float* __restrict__ snapshot, int write_last) {
+                 float* __restrict__ Kstar, double* __restrict__ Kstar64, float* __restrict__ snapshot, int write_last) {
     extern __shared__ float s_raw_all[];  // [groups][Tp]
     __shared__ float s_off_all[kSynthGroups][64];  // per-slice mean (plane kinds) or [0] = volume offset
     __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
@@ -207,10 +207,24 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restric
         __threadfence_block();
         __syncthreads();  // every operator's kernel is in K now
         if (Kstar) {
+            double l1 = 0.0;
             for (int t = tid; t < T; t += blockDim.x) {
                 double acc = 0.0;  // Kstar = sum_g lambda_eff[g] * K_g, float64, fixed order
                 for (int g = 0; g < a.d.n_geneos; ++g) acc += (double)s_lam[g] * (double)K[(size_t)g * T + t];
                 Kstar[t] = (float)acc;
+                if (Kstar64) Kstar64[t] = acc;
+                l1 += fabs(acc);
+            }
+            if (Kstar64) {  // Kstar64[T] = sum_t |Kstar64[t]|: scale of the forward's near-zero test (fixed-order block sum)
+                __shared__ double s_l1[kSynthThreads * kSynthGroups / 32];
+                l1 = warp_sum(l1);
+                if (lane == 0) s_l1[tid >> 5] = l1;
+                __syncthreads();
+                if (tid == 0) {
+                    double tot = 0.0;
+                    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_l1[w];
+                    Kstar64[T] = tot;
+                }
             }
         }
         if (lambda_eff && tid < a.d.n_geneos) lambda_eff[tid] = s_lam[tid];
@@ -377,7 +391,7 @@ static void fill_args(SynthArgs& a, const sn_model_desc* d, const float* const* 
 }  // namespace sn
 
 extern "C" int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const* param_ptrs_host, float* K,
-                                  float* lambda_eff, float* Kstar, float* param_snapshot, int write_last_lambda,
+                                  float* lambda_eff, float* Kstar, double* Kstar64, float* param_snapshot, int write_last_lambda,
                                   void* stream) {
     int rc = sn::check_desc(desc, param_ptrs_host);
     if (rc) return rc;
@@ -391,7 +405,7 @@ extern "C" int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const*
         cudaError_t e = cudaFuncSetAttribute(sn::synth_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return sn::cuda_rc(e);
     }
-    sn::synth_fwd_kernel<<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, param_snapshot, write_last_lambda);
+    sn::synth_fwd_kernel<<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, Kstar64, param_snapshot, write_last_lambda);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

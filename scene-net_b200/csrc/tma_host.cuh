@@ -29,7 +29,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // cannot express the tensor (caller falls back to plain loads).
 inline bool make_grid_tmap(CUtensorMap* m, const float* x, int B, int Z, int X, int Y, int boxZ, int boxX, int boxY) {
     memset(m, 0, sizeof(*m));
-    static const bool disabled = getenv("SN_NO_TMA") != nullptr;  // debugging aid: force the plain-load path
+    static const bool disabled = SN_ENV("SN_NO_TMA") != nullptr;  // debugging aid: force the plain-load path
     if (disabled) return false;
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;

