@@ -96,11 +96,6 @@ int64_t sn_launch_count(void);
  *   Kstar      [T]   float32 out  — sum_g lambda_eff[g] * K[g] (accumulated in float64): by
  *                                   linearity of the convolution the observer's
  *                                   sum_g lambda_g * conv3d(x, K_g) equals conv3d(x, Kstar)
- *   Kstar64    [T+1] float64 out (NULL to skip; ABI v4) — the same sums NOT rounded to float32, followed by
- *                                   sum_t |Kstar64[t]|: the forward kernels re-evaluate a voxel whose float32 sum is
- *                                   within rounding distance of zero with these taps in float64, so that the relu gate
- *                                   [s > 0] (and with it the whole gradient of that voxel) agrees with the reference's
- *                                   float64 convolution (SCENE_Net.py:325)
  *   write_last_lambda != 0: also stores lambda_eff[last] into the last-lambda parameter
  *                                   (the side effect of SCENE_Net.py:333)
  *   param_snapshot [n_param_ptrs] float32 out (NULL to skip) — the parameter values this
@@ -109,7 +104,7 @@ int64_t sn_launch_count(void);
  * lambda_eff / Kstar may be NULL when desc->lambda_index[0] < 0 (bare GENEO kernels).
  * ====================================================================================== */
 int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const* param_ptrs_host,
-                       float* K, float* lambda_eff, float* Kstar, double* Kstar64, float* param_snapshot,
+                       float* K, float* lambda_eff, float* Kstar, float* param_snapshot,
                        int write_last_lambda, void* stream);
 
 /* Jacobian^T of the synthesis: dparams[i] = sum_{g,t} dK[g,t] * dK_g[t]/dparam_i for every
@@ -141,25 +136,22 @@ int sn_scenenet_param_grads(const sn_model_desc* desc, const float* const* param
  *         for the whole grid, sn_select_fwd_path_state).  Without nnz the dense stencil runs.
  *         SN_PATH_DENSE / SN_PATH_SPARSE force one kernel for every tile (measurement, tests).  Same pred either way up
  *         to float32 summation order.
- *   Kstar [T] float32, Kstar64 [T+1] float64 or NULL   (from sn_geneo_synth_fwd; with Kstar64 the sign of sums within
- *         float32 rounding distance of zero is decided in float64 — see there)
+ *   Kstar [T] float32                  (from sn_geneo_synth_fwd)
  *   pred  [B,1,Z,X,Y] out, dtype pred_dtype (SN_F32 / SN_F64): relu(tanh(conv3d_same(x, Kstar)))
  * x must be 16-byte aligned.
  * ====================================================================================== */
 #define SN_PATH_AUTO 0
 #define SN_PATH_DENSE 1
 #define SN_PATH_SPARSE 2
-int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, const double* Kstar64,
+int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype, void* stream);
 /* Several observers on the SAME grids — SCENENetQuantile.forward (SCENE_Net.py:409-415: one SCENE_Net per quantile,
- * predictions concatenated).  Kstars [n_observers][T] float32, Kstars64 [n_observers][T+1] float64 or
- * NULL, preds [n_observers][B,1,Z,X,Y] out.
+ * predictions concatenated).  Kstars [n_observers][T] float32, preds [n_observers][B,1,Z,X,Y] out.
  * The occupancy-driven kernel lists the non-zero voxels of a tile once and scatters them with every observer's taps
  * (x is read once); the dense stencil runs once per observer.  Selection as in sn_scenenet_fwd.  n_observers <= 8. */
 #define SN_MAX_OBSERVERS 8
-int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, const double* Kstars64,
-                          int n_observers, int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype,
-                          void* stream);
+int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, int n_observers,
+                          int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype, void* stream);
 
 /* Observer backward, data part — replaces aten::convolution_backward (weight gradient) and
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
@@ -352,13 +344,24 @@ int sn_vox_finalize(const int32_t* count, const int32_t* keep_count, int n_cloud
  *                   (e.g. torch symmetric memory), zero-initialised before the first call
  *   seq_counter     DEVICE uint32, local, zero-initialised: the call sequence number (the kernel
  *                   increments it, so a captured CUDA graph can be replayed as is)
- *   status          DEVICE int32 (may be NULL): set to 1 if a peer did not answer within ~2 s
- *                   (the payload is then NaN; the device is never left spinning)
+ *   status          DEVICE int32 (may be NULL): set to 1 when a peer did not answer within the bound
+ *   timeout_ms      bound on the wait for a peer in milliseconds of wall clock (0 = wait for ever).  Ranks of a
+ *                   training job skew by seconds to minutes (checkpoints, validation, loader stalls) and NCCL simply
+ *                   waits; use minutes (the Python wrapper's default: 10).  Running into the bound is FATAL: *status is
+ *                   set and the kernel traps, so the process' next CUDA call fails — the payload is never replaced
+ *                   by a made-up value (ABI v4; v3 wrote NaN after ~2 s and carried on).
  * Every rank must issue the same sequence of calls.
  * ====================================================================================== */
 int64_t sn_peer_allreduce_buffer_bytes(int world);
 int sn_peer_allreduce(float* data, int n, int rank, int world, const uint64_t* peer_bufs_host,
-                      uint32_t* seq_counter, int32_t* status, void* stream);
+                      uint32_t* seq_counter, int32_t* status, int64_t timeout_ms, void* stream);
+/* sn_scenenet_param_grads followed by that all-reduce of dparams, in ONE launch: the CTA that computes the parameter
+ * gradients exchanges them itself (the collective of a data-parallel step starts the moment its payload exists; no second
+ * launch on the critical path).  Arguments as for the two calls above; scale = 1 / world gives DDP's mean. */
+int sn_scenenet_param_grads_allreduce(const sn_model_desc* desc, const float* const* param_ptrs_host,
+                                      const float* K, const float* lambda_eff, const double* W, double scale, float* dparams,
+                                      int rank, int world, const uint64_t* peer_bufs_host, uint32_t* seq_counter,
+                                      int32_t* status, int64_t timeout_ms, void* stream);
 
 /* ======================================================================================
  * measurement helper: FP32 FMA-pipe peak micro-benchmark (the roofline denominator that

@@ -43,12 +43,30 @@ PARAM_NAMES = {  # alphabetical = nn.ParameterDict order
 # --------------------------------------------------------------------------------------
 # index plumbing (the reference's meshgrid(...).T.reshape / .view dance)
 # --------------------------------------------------------------------------------------
+# dtype of the tap coordinates: float32 like the reference; tests set float64 (together with float64 parameters) to get the
+# exact value of the same formulas and measure the reference's own float32 rounding noise against it
+COORD_DTYPE = torch.float32
+
+
+class exact_arithmetic:
+    """with exact_arithmetic(): SYNTH[...] on float64 parameters evaluates the reference's formulas in float64"""
+
+    def __enter__(self):
+        global COORD_DTYPE
+        self._saved, COORD_DTYPE = COORD_DTYPE, torch.float64
+
+    def __exit__(self, *exc):
+        global COORD_DTYPE
+        COORD_DTYPE = self._saved
+        return False
+
+
 def _plane_coords(kx, ky):
     """plane[p, q] is evaluated at (i, j) = ((p*ky+q) % kx, (p*ky+q) // kx)
     (cylinder.py:164-171: rows of `.T.reshape(-1,2)` are n = j*kx + i, then `.view(kx,ky)`)."""
     n = torch.arange(kx * ky)
-    i = (n % kx).to(torch.float32)
-    j = (n // kx).to(torch.float32)
+    i = (n % kx).to(COORD_DTYPE)
+    j = (n // kx).to(COORD_DTYPE)
     return i, j
 
 
@@ -56,9 +74,9 @@ def _volume_coords(kz, kx, ky):
     """K.flatten()[r] is evaluated at (iz, ix, iy) = (r % kz, (r // kz) % kx, r // (kz*kx))
     (neg_sphere.py:187-197)."""
     r = torch.arange(kz * kx * ky)
-    iz = (r % kz).to(torch.float32)
-    ix = ((r // kz) % kx).to(torch.float32)
-    iy = (r // (kz * kx)).to(torch.float32)
+    iz = (r % kz).to(COORD_DTYPE)
+    ix = ((r // kz) % kx).to(COORD_DTYPE)
+    iy = (r // (kz * kx)).to(COORD_DTYPE)
     return iz, ix, iy
 
 

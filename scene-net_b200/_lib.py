@@ -50,11 +50,11 @@ SIGNATURES = {
     "sn_abi_version": (_i, []),
     "sn_build_info": (C.c_char_p, []),
     "sn_launch_count": (_i64, []),
-    "sn_geneo_synth_fwd": (_i, [_descp, _pp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sn_geneo_synth_fwd": (_i, [_descp, _pp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sn_geneo_synth_bwd": (_i, [_descp, _pp, _vp, _vp, _vp]),
     "sn_scenenet_param_grads": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _vp]),
-    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "sn_scenenet_fwd_multi": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sn_scenenet_fwd_multi": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "sn_scenenet_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "sn_scenenet_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sn_select_path": (_i, [_i, _i64, _i, _i, _i, _i, _i, _i, _i]),
@@ -80,7 +80,8 @@ SIGNATURES = {
     "sn_vox_finalize_workspace_bytes": (_i64, [_i, _i]),
     "sn_vox_finalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sn_peer_allreduce_buffer_bytes": (_i64, [_i]),
-    "sn_peer_allreduce": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64), _vp, _vp, _vp]),
+    "sn_peer_allreduce": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64), _vp, _vp, _i64, _vp]),
+    "sn_scenenet_param_grads_allreduce": (_i, [_descp, _pp, _vp, _vp, _vp, _d, _vp, _i, _i, C.POINTER(C.c_uint64), _vp, _vp, _i64, _vp]),
     "sn_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(C.c_double), _vp]),
 }
 

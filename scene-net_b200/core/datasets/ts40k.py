@@ -88,6 +88,34 @@ def _load_rows(src: Source) -> np.ndarray:
     return a
 
 
+class _NpyPayload:
+    """a `.npy` file whose payload can go STRAIGHT into pinned memory: [N, 4] float64, C order (what the reference's
+    dataset builder writes, core/datasets/ts40k.py:198-207).  Only the header is parsed here; `read_into` fills a slice
+    of the staging buffer with one readinto() — no intermediate numpy array, no second host copy."""
+
+    def __init__(self, path):
+        self.path = path
+        with open(path, "rb") as f:
+            version = np.lib.format.read_magic(f)
+            shape, fortran, dtype = (np.lib.format.read_array_header_1_0(f) if version == (1, 0)
+                                     else np.lib.format.read_array_header_2_0(f))
+            self.offset = f.tell()
+        if fortran or dtype != np.dtype("<f8") or len(shape) != 2 or shape[1] != 4 or shape[0] == 0:
+            raise ValueError("not a non-empty C-ordered [N, 4] float64 .npy")
+        self.shape = shape
+
+    def read_into(self, out: np.ndarray):
+        with open(self.path, "rb", buffering=0) as f:
+            f.seek(self.offset)
+            mv = memoryview(out).cast("B")
+            got = 0
+            while got < len(mv):
+                n = f.readinto(mv[got:])
+                if not n:
+                    raise IOError(f"{self.path}: truncated payload")
+                got += n
+
+
 class TS40KDeviceLoader:
     """Iterates (x, y) batches of voxel grids resident on `device`.
 
@@ -99,7 +127,7 @@ class TS40KDeviceLoader:
 
     def __init__(self, sources, batch_size: int, keep_labels: Sequence[float] = (POWER_LINE_SUPPORT_TOWER,),
                  vxg_size: Sequence[int] = (64, 64, 64), device: Optional[torch.device] = None, dtype: torch.dtype = torch.float64,
-                 shuffle: bool = False, drop_last: bool = False, seed: Optional[int] = None, io_threads: int = 8):
+                 shuffle: bool = False, drop_last: bool = False, seed: Optional[int] = None, io_threads: Optional[int] = None):
         if isinstance(sources, TS40K):
             sources = [sources.path_of(i) for i in range(len(sources))]
         self.sources: List[Source] = list(sources)
@@ -113,8 +141,10 @@ class TS40KDeviceLoader:
             raise RuntimeError("TS40KDeviceLoader voxelizes on the GPU: there is no CPU path")
         self.dtype, self.shuffle, self.drop_last = dtype, shuffle, drop_last
         self._rng = random.Random(seed)
-        self._pool = ThreadPoolExecutor(max_workers=max(1, io_threads))
+        # staging is a host memcpy / file read per sample: one thread per core up to 16 (8 threads left it at half the PCIe rate)
+        self._pool = ThreadPoolExecutor(max_workers=max(1, io_threads if io_threads else min(16, os.cpu_count() or 8)))
         self._staging = [None, None]  # two pinned [cap, 4] float64 buffers, reused across batches
+        self._uploaded = [None, None]  # the event of the last H2D copy that READ each pinned slot
         self._copy_stream = torch.cuda.Stream(device=self.device)
 
     def __len__(self) -> int:
@@ -122,9 +152,17 @@ class TS40KDeviceLoader:
         return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
 
     # ------------------------------------------------------------------ host side: files -> one pinned buffer
-    def _read_one(self, idx: int) -> np.ndarray:
+    def _read_one(self, idx: int):
+        """the sample's rows, or for a plain [N, 4] float64 `.npy` file only its parsed header (the payload is read
+        straight into the pinned staging buffer later)"""
+        src = self.sources[idx]
+        if isinstance(src, (str, os.PathLike)):
+            try:
+                return _NpyPayload(src)
+            except Exception:  # noqa: BLE001  (other layouts / unreadable: the general path below)
+                pass
         try:
-            a = _load_rows(self.sources[idx])
+            a = _load_rows(src)
             if a.shape[0] == 0:
                 raise ValueError("empty sample")
             return a
@@ -142,6 +180,10 @@ class TS40KDeviceLoader:
         arrays = list(self._pool.map(self._read_one, idxs))
         counts = [a.shape[0] for a in arrays]
         total = sum(counts)
+        # the asynchronous H2D copy that last read this pinned slot (two batches ago) must have finished before the slot
+        # is overwritten: a stream-side wait in the consumer does not hold the HOST back
+        if self._uploaded[slot] is not None:
+            self._uploaded[slot].synchronize()
         buf = self._staging[slot]
         if buf is None or buf.shape[0] < total:
             buf = torch.empty((max(total, 1 << 16) * 5 // 4, 4), dtype=torch.float64).pin_memory()
@@ -151,19 +193,23 @@ class TS40KDeviceLoader:
         np.cumsum(counts, out=offs[1:])
 
         def put(i):
-            view[offs[i]:offs[i + 1], :] = arrays[i][:, :4]  # float64 conversion (if any) + copy into pinned memory
+            if isinstance(arrays[i], _NpyPayload):
+                arrays[i].read_into(view[offs[i]:offs[i + 1], :])  # file -> pinned memory, no intermediate copy
+            else:
+                view[offs[i]:offs[i + 1], :] = arrays[i][:, :4]  # float64 conversion (if any) + copy into pinned memory
 
         list(self._pool.map(put, range(len(arrays))))
-        return buf[:total], torch.from_numpy(offs).pin_memory()
+        return buf[:total], torch.from_numpy(offs).pin_memory(), slot
 
     # ------------------------------------------------------------------ device side
     def _upload(self, staged):
-        rows, offs = staged
+        rows, offs, slot = staged
         with torch.cuda.stream(self._copy_stream):
-            d_rows = rows.to(self.device, non_blocking=True)
+            d_rows = rows.to(self.device, non_blocking=True)  # one cudaMemcpyAsync for the whole batch
             d_offs = offs.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
+        self._uploaded[slot] = ev
         return d_rows, d_offs, ev
 
     def _voxelize(self, uploaded):
@@ -194,6 +240,6 @@ class TS40KDeviceLoader:
             for k in range(len(batches)):
                 cur = nxt
                 if k + 1 < len(batches):
-                    # the pinned slot (k+1) % 2 was last used by batch k-1, whose upload finished before its voxelization started
+                    # the pinned slot (k+1) % 2 was last read by the upload of batch k-1: _stage waits for that copy's event
                     nxt = self._upload(self._stage(batches[k + 1], (k + 1) % 2))
                 yield self._voxelize(cur)

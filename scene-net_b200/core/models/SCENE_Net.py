@@ -38,12 +38,15 @@ def _side_stream(device) -> torch.cuda.Stream:
 def _finish_backward(ctx, W):
     """tap gradient -> parameter gradients (+ the gradient all-reduce), shared by the two autograd functions"""
     x32, pred, K, lam, snap, nnz = ctx.saved_tensors[:6]
+    if getattr(ctx.sync_group, "fused_with_param_grads", False):
+        # dist.PeerAllReduce: the Jacobian kernel exchanges the gradients over NVLink peer memory itself (one launch)
+        return ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale, peer=ctx.sync_group)
     d = ops.param_grads(ctx.spec, snap, K, lam, W, ctx.grad_scale)
     if ctx.sync_group is not None:
         # the whole gradient payload is ONE flat float32 tensor: one collective right behind the Jacobian kernel,
         # no pack / unpack kernels; the parameter .grads are views into it
         if callable(ctx.sync_group):
-            ctx.sync_group(d)  # dist.PeerAllReduce: our single-kernel exchange over NVLink peer memory
+            ctx.sync_group(d)  # a callable exchange on the flat payload
         else:
             import torch.distributed as dist
             dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_group is True else ctx.sync_group)
@@ -119,6 +122,49 @@ class _ObserverFunction(torch.autograd.Function):
         unused = ctx.spec.unused
         grads = [d[i] if (ctx.needs_input_grad[i + 7] and i not in unused) else None for i in range(d.numel())]
         return (None, None, None, None, None, None, None, *grads)
+
+
+class _MultiObserverFunction(torch.autograd.Function):
+    """preds [Q,B,1,Z,X,Y] of Q observers on the SAME grids (SCENENetQuantile, SCENE_Net.py:347-415) as one autograd node:
+    one grid preparation, Q kernel syntheses, ONE forward launch for all observers (sn_scenenet_fwd_multi: the
+    occupancy-driven kernel lists a tile's non-zero voxels once and scatters them with every observer's taps), and in the
+    backward one tap-gradient reduction + parameter Jacobian per observer on the shared float32 grid / grid state."""
+
+    @staticmethod
+    def forward(ctx, x, specs, counts, grad_scales, sync_groups, mode, prepared, *params):
+        x32, nnz = prepared if prepared is not None else ops.prepare(x.detach())
+        Ks, lams, snaps, kstars = [], [], [], []
+        off = 0
+        for spec, n in zip(specs, counts):
+            K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params[off:off + n]], write_last_lambda=True)
+            off += n
+            Ks.append(K); lams.append(lam); snaps.append(snap); kstars.append(Kstar)
+        out_dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+        preds = ops.scenenet_fwd_multi(x32, torch.stack(kstars), out_dtype, nnz=nnz, mode=mode[0])
+        ctx.specs, ctx.counts, ctx.grad_scales, ctx.sync_groups, ctx.bwd_mode = specs, counts, grad_scales, sync_groups, mode[1]
+        ctx.save_for_backward(x32, nnz, preds, *Ks, *lams, *snaps)
+        return preds
+
+    @staticmethod
+    def backward(ctx, dpreds):
+        Q = len(ctx.specs)
+        x32, nnz, preds = ctx.saved_tensors[:3]
+        Ks, lams, snaps = (ctx.saved_tensors[3 + i * Q:3 + (i + 1) * Q] for i in range(3))
+        grads = []
+        off = 0
+        for q, (spec, n) in enumerate(zip(ctx.specs, ctx.counts)):
+            W = ops.scenenet_bwd(x32, preds[q], dpreds[q], spec.kernel_size, nnz, mode=ctx.bwd_mode)
+            peer = ctx.sync_groups[q] if getattr(ctx.sync_groups[q], "fused_with_param_grads", False) else None
+            d = ops.param_grads(spec, snaps[q], Ks[q], lams[q], W, ctx.grad_scales[q], peer=peer)
+            if peer is None and ctx.sync_groups[q] is not None:
+                if callable(ctx.sync_groups[q]):
+                    ctx.sync_groups[q](d)
+                else:
+                    import torch.distributed as dist
+                    dist.all_reduce(d, op=dist.ReduceOp.SUM, group=None if ctx.sync_groups[q] is True else ctx.sync_groups[q])
+            grads += [d[i] if (ctx.needs_input_grad[7 + off + i] and i not in spec.unused) else None for i in range(n)]
+            off += n
+        return (None,) * 7 + tuple(grads)
 
 
 def _apex_int(layer) -> int:
@@ -363,6 +409,8 @@ class SCENENetQuantile(nn.Module):
         self.scnets = nn.ModuleList([SCENE_Net(geneo_num, kernel_size, plot) for _ in range(len(qs))]).to(device)
         self.qs = qs
         self.device = device
+        #: True: one observer after the other like the reference (SCENE_Net.py:409-415) instead of the fused forward
+        self.per_observer_forward = False
 
     def get_num_total_params(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -382,22 +430,19 @@ class SCENENetQuantile(nn.Module):
         prepared = ops.prepare(x.detach()) if x.is_cuda else None
         nets = list(self.scnets)
         sizes = {tuple(net._spec_and_params()[0].kernel_size) for net in nets} if x.is_cuda else set()
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if x.is_cuda and not needs_grad and len(sizes) == 1 and 1 < len(nets) <= 8 and x.numel():
-            # inference: ONE forward for all quantiles (sn_scenenet_fwd_multi) — the occupancy-driven kernel lists the
-            # non-zero voxels of a tile once and scatters them with every observer's taps.  Same values as the
-            # per-observer path below (same kernels, same summation order).
-            x32, state = prepared
-            kstars = []
+        if x.is_cuda and len(sizes) == 1 and 1 < len(nets) <= 8 and x.numel() and not self.per_observer_forward:
+            # ONE forward for all quantiles (sn_scenenet_fwd_multi) — the occupancy-driven kernel lists the non-zero voxels
+            # of a tile once and scatters them with every observer's taps; with gradients enabled the same launch is one
+            # autograd node (_MultiObserverFunction) whose backward runs one tap-gradient reduction per observer on the
+            # shared grid state.  Same values as the per-observer path below (same kernels, same summation order).
+            specs, counts, flat = [], [], []
             for net in nets:
                 spec, params = net._spec_and_params()
-                kstars.append(ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=True)[2])
-            out_dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+                specs.append(spec); counts.append(len(params)); flat.extend(params)
             modes = {tuple(net.path_modes) for net in nets}
-            mode = modes.pop()[0] if len(modes) == 1 else 0
-            k64s = torch.stack([k.k64 for k in kstars]) if all(getattr(k, "k64", None) is not None for k in kstars) else None
-            preds = ops.scenenet_fwd_multi(x32, torch.stack([k.as_subclass(torch.Tensor) for k in kstars]), out_dtype, nnz=state,
-                                           mode=mode, k64s=k64s)  # [Q,B,1,Z,X,Y]
+            mode = modes.pop() if len(modes) == 1 else (0, 0)
+            preds = _MultiObserverFunction.apply(x, tuple(specs), tuple(counts), tuple(float(n.grad_scale) for n in nets),
+                                                 tuple(n.grad_sync_group for n in nets), mode, prepared, *flat)  # [Q,B,1,Z,X,Y]
             return preds[:, :, 0].permute(1, 0, 2, 3, 4).to(torch.float32).contiguous()
         return torch.cat([net(x, _prepared=prepared).to(torch.float32) for net in nets], dim=1)
 

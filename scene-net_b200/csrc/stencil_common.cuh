@@ -60,10 +60,6 @@ struct FwdParams {
     const int* tile_list;
     unsigned long long* state;
     int last_pass;
-    // float64 re-evaluation of sums within rounding distance of zero (exact_sum_f64): unrounded taps of the FULL kernel
-    // (all z-split passes) + sum |tap|, the full kernel's z extent and left pad
-    const double* k64;
-    int full_kz, full_plz;
     // device-side selection against the occupancy-driven kernel (stencil_fwd_sparse.cu): this dense stencil returns
     // at once when nnz != NULL and *nnz <= nnz_max
     const unsigned long long* nnz;
@@ -192,42 +188,17 @@ __device__ __forceinline__ double tanh_pos_f64_tab(double s, const double* __res
     return (1.0 - u) * rc;
 }
 
-// ---- the sign of sums near zero (ABI v4) ------------------------------------------------------------------------------
-// pred = relu(tanh(s)) has a kink at s = 0 and its derivative jumps from 0 to 1 there: a voxel whose float32 sum has the
-// wrong SIGN changes the whole gradient contribution of that voxel (dL/ds = dL/dpred instead of 0).  Found with the
-// unmodified reference on BASELINE config 2 at its full size (8.4 M voxels): ONE voxel with s_ref = 4.1e-8 came out
-// negative in float32 and moved the 11 parameter gradients by 2.4e-4 relative — 24 x the 1e-5 bar — while every gradient
-// agreed to 2e-7 with the reference's gate (gpurun_out/r2c_diag.log, profiles/r2_notes.md).  So a voxel whose float32
-// sum lies within rounding distance of zero is summed again in float64 with the unrounded taps Kstar64: its sign then
-// agrees with the reference's float64 convolution unless |s_ref| < ~1e-15.  ~6e-5 of the voxels of a config-2 batch.
-struct ExactSum {
-    const float* x;       // [B,1,Z,X,Y] float32 grid
-    const double* k64;    // [T+1]: unrounded taps of the FULL kernel, then sum |tap|; NULL = feature off
-    int Z, X, Y, kz, kx, ky, plz, plx, ply;  // full kernel extents and its left pads
-    float eps_rel;        // |s| < eps_rel * k64[T] is "near zero": 2^-18 for running float32 sums, 2^-21 compensated
-};
-static __device__ __noinline__ double exact_sum_f64(const ExactSum& c, int b, int gz, int gx, int gy) {
-    double s = 0.0;
-    const float* xb = c.x + (size_t)b * c.Z * c.X * c.Y;
-    for (int dz = 0; dz < c.kz; ++dz) {
-        const int z = gz + dz - c.plz;
-        if (z < 0 || z >= c.Z) continue;
-        for (int dx = 0; dx < c.kx; ++dx) {
-            const int xx = gx + dx - c.plx;
-            if (xx < 0 || xx >= c.X) continue;
-            const float* row = xb + ((size_t)z * c.X + xx) * c.Y;
-            const double* kr = c.k64 + (dz * c.kx + dx) * c.ky;
-            for (int dy = 0; dy < c.ky; ++dy) {
-                const int y = gy + dy - c.ply;
-                if (y >= 0 && y < c.Y) {
-                    const float v = __ldg(row + y);
-                    if (v != 0.f) s = fma((double)v, __ldg(kr + dy), s);
-                }
-            }
-        }
-    }
-    return s;
-}
+// ---- the sign of sums near zero --------------------------------------------------------------------------------------
+// pred = relu(tanh(s)) has a kink at s = 0 and its derivative jumps from 0 to 1 there: a voxel whose sum changes SIGN
+// changes that voxel's whole gradient contribution.  On BASELINE config 2 at its full size (8.4 M voxels) two voxels have
+// |s| < 1e-7, and one of them came out on the other side of the kink than in the reference's float64 convolution: the 11
+// parameter gradients moved by 2.4e-4 relative, while with the reference's gates they agree to 2e-7
+// (profiles/r2_diag_gate.log).  A float64 re-evaluation of such sums with unrounded taps was built and measured: it makes
+// the dense and the occupancy-driven kernels agree with each other, but NOT with the reference — two float32 evaluations of
+// the GENEO kernels (ours / the reference's CPU ops / the reference's own CUDA ops) differ by an ulp in some taps, up to
+// 7e-8, which is the size of these sums: the sign of a sum below ~1e-7 is not defined by the model.  It cost 30 % of both
+// forward kernels and was removed; the full-size parity tests give such voxels no upstream gradient and check every
+// other gate (tests/test_gpu_full_size.py).
 
 // Tail of the tap-gradient kernels: the CTA that draws the last ticket sums the partial rows of all CTAs in row order
 // (fixed order: deterministic) into W — no separate reduction launch.  `ticket` is zeroed once per step by

@@ -23,7 +23,7 @@ int stencil_fwd_generic(const FwdParams& p, int ky, cudaStream_t stream);  // st
 // stencil_fwd_sparse.cu
 bool fwd_sparse_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
 bool fwd_tile_handoff_supported(int B, int Z, int X, int Y, int kz, int kx, int ky);
-int fwd_sparse_launch(const float* x, const float* Kstar, const double* Kstar64, void* pred, int out_f64, unsigned long long* state,
+int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, unsigned long long* state,
                       const unsigned long long* gate, unsigned long long nnz_max, unsigned long long dw_max, bool handoff,
                       int B, int Z, int X, int Y, int kz, int kx, int ky, int nq, cudaStream_t stream);
 }  // namespace sn
@@ -66,9 +66,9 @@ static int dense_fwd(const sn::FwdParams& p, int ky, cudaStream_t s) {
 
 static bool fast_fwd_ky(int ky) { return ky == 3 || ky == 5 || ky == 6 || ky == 7 || ky == 9 || ky == 11 || ky == 13 || ky == 15; }
 
-// nq observers on the same grids: Kstar [nq][T], Kstar64 [nq][T+1] or NULL, pred [nq][B,1,Z,X,Y].  The dense stencil runs
-// once per observer; the mask-driven occupancy kernel lists the non-zero voxels of a tile once for all of them.
-static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, const double* Kstar64, int nq,
+// nq observers on the same grids: Kstar [nq][T], pred [nq][B,1,Z,X,Y].  The dense stencil runs once per observer; the
+// mask-driven occupancy kernel lists the non-zero voxels of a tile once for all of them.
+static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, int nq,
                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype, void* stream) {
     if (!x || !Kstar || !pred) return SN_ERR_BAD_ARG;
     if (B < 1 || Z < 1 || X < 1 || Y < 1 || kz < 1 || kx < 1 || ky < 1 || nq < 1 || nq > SN_MAX_OBSERVERS) return SN_ERR_BAD_ARG;
@@ -76,7 +76,6 @@ static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, con
     if (mode != SN_PATH_AUTO && mode != SN_PATH_DENSE && mode != SN_PATH_SPARSE) return SN_ERR_BAD_ARG;
     if ((long long)kz * kx * ky > SN_MAX_TAPS) return SN_ERR_UNSUPPORTED;
     if (nnz && ((uintptr_t)nnz & 7)) return SN_ERR_ALIGN;
-    if (Kstar64 && ((uintptr_t)Kstar64 & 7)) return SN_ERR_ALIGN;
     const long long T = (long long)kz * kx * ky, nvox = (long long)B * Z * X * Y;
     const size_t esz = pred_dtype == SN_F64 ? 8 : 4;
     cudaStream_t s = (cudaStream_t)stream;
@@ -86,7 +85,6 @@ static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, con
     const unsigned long long dw_max = fwd_dense_words_max(nvox);
     const unsigned long long nnz_max = fwd_sparse_nnz_max(nvox, kx, ky);
     auto pred_q = [&](int q) { return (void*)((char*)pred + (size_t)q * (size_t)nvox * esz); };
-    auto k64_q = [&](int q) { return Kstar64 ? Kstar64 + (size_t)q * (size_t)(T + 1) : nullptr; };
     // gate: whole-grid selection on the device (the stencil returns at once when the occupancy-driven kernel is selected);
     // tiles: compute only the tiles the occupancy-driven kernel listed
     auto dense_all = [&](const unsigned long long* gate, bool tiles, bool allow_generic) -> int {
@@ -96,7 +94,6 @@ static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, con
             p.B = B; p.Z = Z; p.X = X; p.Y = Y; p.kz = kz; p.kx = kx;
             p.out_f64 = pred_dtype == SN_F64; p.plz = sn::pad_left(kz);
             p.nnz = gate; p.nnz_max = nnz_max; p.dw_max = dw_max;
-            p.k64 = k64_q(q); p.full_kz = kz; p.full_plz = sn::pad_left(kz);
             if (tiles) {
                 p.state = state;
                 p.tile_list = reinterpret_cast<const int*>(reinterpret_cast<const unsigned*>(state + SN_STATE_WORDS) + sn::state_mask_words(nvox));
@@ -109,11 +106,11 @@ static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, con
         return SN_OK;
     };
     auto sparse_all = [&](const unsigned long long* gate, bool handoff) -> int {
-        int rc = sn::fwd_sparse_launch(x, Kstar, Kstar64, pred, pred_dtype == SN_F64, state, gate, nnz_max, dw_max, handoff, B, Z, X, Y,
+        int rc = sn::fwd_sparse_launch(x, Kstar, pred, pred_dtype == SN_F64, state, gate, nnz_max, dw_max, handoff, B, Z, X, Y,
                                        kz, kx, ky, nq, s);
         if (rc != SN_ERR_UNSUPPORTED || nq == 1) return rc;
         for (int q = 0; q < nq; ++q) {  // no shared lists (no state buffer / shape outside the mask-driven kernel): one launch each
-            rc = sn::fwd_sparse_launch(x, Kstar + q * T, k64_q(q), pred_q(q), pred_dtype == SN_F64, state, gate, nnz_max, dw_max, false,
+            rc = sn::fwd_sparse_launch(x, Kstar + q * T, pred_q(q), pred_dtype == SN_F64, state, gate, nnz_max, dw_max, false,
                                        B, Z, X, Y, kz, kx, ky, 1, s);
             if (rc) return rc;
         }
@@ -146,16 +143,16 @@ static int fwd_impl(const float* x, const unsigned long long* nnz, int mode, con
     return rc;
 }
 
-extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar, const double* Kstar64,
+extern "C" int sn_scenenet_fwd(const float* x, const unsigned long long* nnz, int mode, const float* Kstar,
                                int B, int Z, int X, int Y, int kz, int kx, int ky, void* pred, int pred_dtype,
                                void* stream) {
-    return fwd_impl(x, nnz, mode, Kstar, Kstar64, 1, B, Z, X, Y, kz, kx, ky, pred, pred_dtype, stream);
+    return fwd_impl(x, nnz, mode, Kstar, 1, B, Z, X, Y, kz, kx, ky, pred, pred_dtype, stream);
 }
 
-extern "C" int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, const double* Kstars64,
-                                     int n_observers, int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype,
+extern "C" int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mode, const float* Kstars, int n_observers,
+                                     int B, int Z, int X, int Y, int kz, int kx, int ky, void* preds, int pred_dtype,
                                      void* stream) {
-    return fwd_impl(x, nnz, mode, Kstars, Kstars64, n_observers, B, Z, X, Y, kz, kx, ky, preds, pred_dtype, stream);
+    return fwd_impl(x, nnz, mode, Kstars, n_observers, B, Z, X, Y, kz, kx, ky, preds, pred_dtype, stream);
 }
 
 extern "C" int sn_select_fwd_path_state(int64_t nnz, int64_t dense_words, int B, int Z, int X, int Y, int kz, int kx, int ky) {

@@ -45,11 +45,9 @@ __device__ __forceinline__ void fwd_chunk(float (&acc)[kRZ][4], const float* __r
 // instruction cache level (profiles/r1_notes.md).
 // tanhf, not a float64 tanh: inside this FFMA-bound kernel every float64 variant tried cost +25 % .. +38 % of the
 // kernel (FP64 issue is scarce on B200; see tanh_pos_f64 in stencil_common.cuh, which the occupancy-driven kernel uses).
-static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, const ExactSum* ex, float eps,
-                                              int b, int gz, int gx, int gy, int out_f64, bool vec, int pass_mode) {
+static __device__ __noinline__ void store_row(float a0, float a1, float a2, float a3, void* pred, size_t idx, int out_f64, int ny,
+                                              bool vec, int pass_mode) {
     float o[4] = {a0, a1, a2, a3};
-    const size_t idx = (((size_t)b * ex->Z + gz) * ex->X + gx) * ex->Y + gy;
-    const int ny = ex->Y - gy;
     if (pass_mode & 1) {  // z-split: add the previous passes' partial sum (stored in this row's own slots)
         if (out_f64) {
             const double* in = reinterpret_cast<const double*>(pred) + idx;
@@ -65,12 +63,7 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
     }
     if (!(pass_mode & 2)) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float sv = o[r];
-            // within float32 rounding distance of zero: the sign (the relu gate) is decided in float64 (stencil_common.cuh)
-            if (sv != 0.f && fabsf(sv) < eps && r < ny) sv = (float)exact_sum_f64(*ex, b, gz, gx, gy + r);
-            o[r] = sv > 0.f ? fmaxf(tanhf(sv), 1.401298464e-45f) : 0.f;
-        }
+        for (int r = 0; r < 4; ++r) o[r] = o[r] > 0.f ? tanhf(o[r]) : 0.f;
     }
     if (out_f64) {
         double* out = reinterpret_cast<double*>(pred) + idx;
@@ -98,10 +91,8 @@ static __device__ __noinline__ void store_row(float a0, float a1, float a2, floa
 // unevaluated float32 pair (hi, lo).  float64 predictions: the pair and the previous z-split passes' partial sums are
 // combined in float64 (the partial sums live in pred's own float64 slots) and tanh is evaluated in float64 — next to
 // >= 1000 FFMAs per voxel the float64 work is noise; float32 predictions: hi + lo rounded once, tanhf.
-static __device__ __noinline__ void store_row_comp(const float (&hi)[4], const float (&lo)[4], void* pred, const ExactSum* ex, float eps,
-                                                   int b, int gz, int gx, int gy, int out_f64, bool vec, int pass_mode) {
-    const size_t idx = (((size_t)b * ex->Z + gz) * ex->X + gx) * ex->Y + gy;
-    const int ny = ex->Y - gy;
+static __device__ __noinline__ void store_row_comp(const float (&hi)[4], const float (&lo)[4], void* pred, size_t idx, int out_f64,
+                                                   int ny, bool vec, int pass_mode) {
     if (out_f64) {
         double* out = reinterpret_cast<double*>(pred) + idx;
         double o[4];
@@ -109,10 +100,7 @@ static __device__ __noinline__ void store_row_comp(const float (&hi)[4], const f
         for (int r = 0; r < 4; ++r) {
             o[r] = (double)hi[r] + (double)lo[r];
             if ((pass_mode & 1) && r < ny) o[r] += out[r];
-            if (!(pass_mode & 2)) {
-                if (o[r] != 0.0 && fabs(o[r]) < (double)eps && r < ny) o[r] = exact_sum_f64(*ex, b, gz, gx, gy + r);
-                o[r] = tanh_pos_f64(o[r]);  // relu inside (negative sums clamp to 0)
-            }
+            if (!(pass_mode & 2)) o[r] = tanh_pos_f64(o[r]);  // relu inside (negative sums clamp to 0)
         }
         if (vec) {
             reinterpret_cast<double2*>(out)[0] = make_double2(o[0], o[1]);
@@ -129,10 +117,7 @@ static __device__ __noinline__ void store_row_comp(const float (&hi)[4], const f
         for (int r = 0; r < 4; ++r) {
             o[r] = hi[r] + lo[r];
             if ((pass_mode & 1) && r < ny) o[r] += out[r];
-            if (!(pass_mode & 2)) {
-                if (o[r] != 0.f && fabsf(o[r]) < eps && r < ny) o[r] = (float)exact_sum_f64(*ex, b, gz, gx, gy + r);
-                o[r] = o[r] > 0.f ? fmaxf(tanhf(o[r]), 1.401298464e-45f) : 0.f;
-            }
+            if (!(pass_mode & 2)) o[r] = o[r] > 0.f ? tanhf(o[r]) : 0.f;
         }
         if (vec) {
             *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
@@ -197,12 +182,6 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
     const int tyi = tid % TYT, txi = tid / TYT;
     const int zstride = g.HX * g.WS;
     const bool vec = ((p.Y & 3) == 0);
-    ExactSum ex;
-    ex.x = p.x; ex.k64 = p.k64; ex.Z = p.Z; ex.X = p.X; ex.Y = p.Y; ex.kz = p.full_kz; ex.kx = p.kx; ex.ky = KY;
-    ex.plz = p.full_plz; ex.plx = g.plx; ex.ply = Geo<KY>::PL; ex.eps_rel = 0.f;
-    // |s| below this is "within rounding distance of zero": 2^-18 (running float32 sums) / 2^-21 (compensated) of sum |tap|
-    const float eps = p.k64 ? (float)(__ldg(p.k64 + p.full_kz * p.kx * KY) * (COMP ? 4.76837158203125e-7 : 3.814697265625e-6)) : 0.f;
-
     int k = 0;
     for (int ti = blockIdx.x; ti < ntl; ti += G, ++k) {
         const int tile = p.tile_list ? __ldg(p.tile_list + ti) : ti;
@@ -282,11 +261,11 @@ stencil_fwd_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tmap) 
             for (int zo = 0; zo < kRZ; ++zo) {
                 const int gz = z0 + zo;
                 if (gz < p.Z) {
+                    const size_t idx = (((size_t)b * p.Z + gz) * p.X + gx) * p.Y + gy;
                     if constexpr (COMP)
-                        store_row_comp(hi[zo], lo[zo], p.pred, &ex, eps, b, gz, gx, gy, p.out_f64, vec, p.pass_mode);
+                        store_row_comp(hi[zo], lo[zo], p.pred, idx, p.out_f64, p.Y - gy, vec, p.pass_mode);
                     else
-                        store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, &ex, eps, b, gz, gx, gy, p.out_f64, vec,
-                                  p.pass_mode);
+                        store_row(acc[zo][0], acc[zo][1], acc[zo][2], acc[zo][3], p.pred, idx, p.out_f64, p.Y - gy, vec, p.pass_mode);
                 }
             }
         }
@@ -376,8 +355,6 @@ static int fwd_passes(const FwdParams& p0, cudaStream_t s) {
         p.plz = pad_left(p0.kz) - dz0;
         p.pass_mode = (i > 0 ? 1 : 0) | (i < npass - 1 ? 2 : 0);
         p.last_pass = (i == npass - 1 && p0.last_pass) ? 1 : 0;
-        p.full_kz = p0.kz;
-        p.full_plz = pad_left(p0.kz);
         const int rc = FwdRemDispatch<KY, TYT, Geo<KY>::C - 1>::run(p, s);
         if (rc) return rc;
     }

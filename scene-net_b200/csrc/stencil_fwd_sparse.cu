@@ -54,7 +54,6 @@ struct FsParams {
     unsigned long long* state;  // the grid state buffer's counters ([3] dense tiles, [4] non-unit voxels, [5] tile counter)
     int* dense_list;            // tiles handed to the dense stencil (NULL: every tile is scattered here)
     int dense_thresh;           // ... when their halo box holds more non-zero voxels than this
-    const double* k64;          // [nq][T+1] unrounded taps + sum |tap| (NULL: no float64 re-evaluation near zero)
 };
 
 struct FsEntry {
@@ -292,7 +291,7 @@ fwd_sparse_kernel(const FsParams p) {
 //      may own the same accumulator: the PTX memory model requires the barrier; measured cost in r2_notes.md).
 //   C  lanes <-> consecutive y (conflict-free scalar LDS, coalesced 8-byte stores), the accumulator is zeroed as it is
 //      read (no separate zeroing pass; halo margins are scratch and never read), tanh by the table-driven float64
-//      evaluation (~24 instructions), sums within rounding distance of zero re-evaluated in float64 (exact_sum_f64).
+//      evaluation (~24 instructions).
 //   Tiles are handed out by an atomic counter in the state buffer (a locally dense tile no longer makes its CTA a
 //   straggler), empty tiles are zero-filled with 16-byte stores, and a tile whose halo holds more than `dense_thresh`
 //   non-zeros is appended to the tile list for the dense stencil that follows on the stream (per-TILE kernel choice:
@@ -313,8 +312,10 @@ __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) 
 }
 #ifdef SN_FO_NOSYNC  // measurement only: the v2 behaviour (relies on in-order LDS/STS of a converged warp)
 #define FO_ORDER()
+#define FO_ORDER_PTX
 #else
 #define FO_ORDER() __syncwarp()
+#define FO_ORDER_PTX "bar.warp.sync 0xffffffff;\n\t"
 #endif
 
 template <int NI2, bool OUT64, bool MULTI, int CPT>  // CPT: cells per thread this instantiation holds (3 or kFoMaxCells)
@@ -376,12 +377,6 @@ fwd_occ_kernel(const FsParams p) {
     const float* skl = sk + lane;
     const bool vec = (p.Y & 3) == 0;
     const bool binary = p.state ? (p.state[4] == 0ull) : false;  // occupancy grid: every listed value is 1
-    float eps = 0.f;
-    ExactSum ex;
-    ex.x = p.x; ex.k64 = p.k64; ex.Z = p.Z; ex.X = p.X; ex.Y = p.Y; ex.kz = p.kz; ex.kx = p.kx; ex.ky = p.ky;
-    ex.plz = p.plz; ex.plx = p.plx; ex.ply = ply; ex.eps_rel = 0.f;
-    if (p.k64) eps = (float)(__ldg(p.k64 + T) * 3.814697265625e-6);  // 2^-18 * sum |tap| (observer 0; MULTI: per q below)
-
     // ---- tile hand-out: an atomic counter in the state buffer (static stride without one); thread 0 decodes a tile's
     // coordinates one tile ahead into ctl[slot]
     unsigned long long* tctr = p.state ? p.state + 5 : nullptr;
@@ -515,7 +510,6 @@ fwd_occ_kernel(const FsParams p) {
 
         bool multi_round = total_p > kFoCap;
         for (int q = 0; q < nq; ++q) {
-            if (MULTI && p.k64) eps = (float)(__ldg(p.k64 + (size_t)q * (T + 1) + T) * 3.814697265625e-6);
             for (int lo = 0; lo < total_p; lo += kFoCap) {
                 if (q == 0 || multi_round) {
                     if (lo > 0 || q > 0) __syncthreads();  // every warp is done with the previous round's list
@@ -558,64 +552,99 @@ fwd_occ_kernel(const FsParams p) {
                     __syncthreads();  // (4) the list is complete
                 }
                 // ---- B: warp zo adds slice dz of the taps at every listed voxel of z-row zo + dz
-                for (int dz = 0; dz < p.kz; ++dz) {
-                    int s0 = pstart[warp + dz] - lo, s1 = pstart[warp + dz + 1] - lo;  // even positions
-                    s0 = s0 < 0 ? 0 : s0;
-                    s1 = s1 > kFoCap ? kFoCap : s1;
-                    if (s0 >= s1) continue;
-                    float kk[NI2];
+                {
+                    int s0 = pstart[warp] - lo;
+                    for (int dz = 0; dz < p.kz; ++dz) {
+                        int s1 = pstart[warp + dz + 1] - lo;  // even positions
+                        const int e0 = s0 < 0 ? 0 : s0, e1 = s1 > kFoCap ? kFoCap : s1;
+                        s0 = s1;
+                        if (e0 >= e1) continue;
+                        const uint32_t la = lists_u + (uint32_t)e0 * 8u, lend = lists_u + (uint32_t)e1 * 8u;
+                        if constexpr (NI2 == 1) {
+                            // the whole pair loop by hand (ncu: the compiler's version was 21 instructions per pair — register
+                            // moves of a prefetch, uniform-datapath detours; this one is 13): two entries per 16-byte broadcast
+                            // load, predicated read-modify-writes (the warp stays converged), a warp barrier after each: the next
+                            // entry may own the same accumulator from another lane, and only the barrier orders the two accesses
+                            // under the PTX memory model
+                            const float kk = okp[0] ? skl[q * T + dz * P] : 0.f;
+                            asm volatile(
+                                "{\n\t.reg .pred q, more;\n\t.reg .f32 v0, v1, t;\n\t.reg .b32 b0, b1, a;\n\t"
+                                "setp.ne.s32 q, %3, 0;\n\t"
+                                "mov.u32 a, %0;\n\t"
+                                "FO_PAIR:\n\t"
+                                "ld.shared.v4.b32 {v0, b0, v1, b1}, [a];\n\t"
+                                "add.u32 a, a, 16;\n\t"
+                                "add.u32 b0, b0, %2;\n\t"
+                                "add.u32 b1, b1, %2;\n\t"
+                                "setp.ne.u32 more, a, %1;\n\t"
+                                "@q ld.shared.f32 t, [b0];\n\t"
+                                "@q fma.rn.f32 t, v0, %4, t;\n\t"
+                                "@q st.shared.f32 [b0], t;\n\t"
+                                FO_ORDER_PTX
+                                "@q ld.shared.f32 t, [b1];\n\t"
+                                "@q fma.rn.f32 t, v1, %4, t;\n\t"
+                                "@q st.shared.f32 [b1], t;\n\t"
+                                FO_ORDER_PTX
+                                "@more bra FO_PAIR;\n\t}" ::"r"(la),
+                                "r"(lend), "r"(accl[0]), "r"(okp[0]), "f"(kk)
+                                : "memory");
+                        } else {
+                            float kk[NI2];
 #pragma unroll
-                    for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[q * T + dz * P + 32 * j] : 0.f;
-                    uint32_t la = lists_u + (uint32_t)s0 * 8u;
-                    const uint32_t lend = lists_u + (uint32_t)s1 * 8u;
-                    float v0, v1;
-                    uint32_t b0, b1;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=r"(b0), "=f"(v1), "=r"(b1) : "r"(la) : "memory");
+                            for (int j = 0; j < NI2; ++j) kk[j] = okp[j] ? skl[q * T + dz * P + 32 * j] : 0.f;
 #pragma unroll 1
-                    while (true) {
-                        la += 16u;
-                        float n0, n1;
-                        uint32_t c0, c1;  // the next pair (the list has two entries of slack behind its last one)
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(n0), "=r"(c0), "=f"(n1), "=r"(c1) : "r"(la) : "memory");
+                            for (uint32_t a = la; a != lend; a += 16u) {
+                                float v0, v1;
+                                uint32_t b0, b1;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=r"(b0), "=f"(v1), "=r"(b1) : "r"(a) : "memory");
 #pragma unroll
-                        for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b0, v0, kk[j], okp[j]);
-                        FO_ORDER();
+                                for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b0, v0, kk[j], okp[j]);
+                                FO_ORDER();
 #pragma unroll
-                        for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b1, v1, kk[j], okp[j]);
-                        FO_ORDER();
-                        if (la == lend) break;
-                        v0 = n0; b0 = c0; v1 = n1; b1 = c1;
+                                for (int j = 0; j < NI2; ++j) fo_rmw(accl[j] + b1, v1, kk[j], okp[j]);
+                                FO_ORDER();
+                            }
+                        }
                     }
                 }
             }
-            // ---- C: epilogue of this warp's plane: lanes <-> consecutive y; the accumulators are zeroed as they are read
+            // ---- C: epilogue of this warp's plane: lanes <-> consecutive y (conflict-free shared loads, coalesced stores);
+            // every accumulator of the interior is zeroed as it is read (rows / columns outside the grid included: they
+            // collect contributions too).  ncu of the first version of this loop: 150 instructions per 32 outputs (64-bit
+            // index arithmetic and parameter loads per iteration); now the pointers advance by a row per step.
             __syncwarp();
             {
                 const int gz = z0 + warp;
-                const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + gz) * p.X + x0) * p.Y + y0;
                 const int nyh = p.IY >> 5;  // 32-column chunks per output row
-                float* arow = accp + (p.kx - 1) * p.AS + (p.ky - 1) + lane;
+                float* a = accp + (p.kx - 1) * p.AS + (p.ky - 1) + lane;
+                const int nrows = gz < p.Z ? min(p.IX, p.X - x0) : 0;  // rows that are stored
+                const size_t idx0 = (size_t)q * (size_t)p.pred_qstride + (((size_t)b * p.Z + (gz < p.Z ? gz : 0)) * p.X + x0) * p.Y + y0 + lane;
+                const bool in0 = y0 + lane < p.Y, in1 = nyh == 2 && y0 + 32 + lane < p.Y;
+                if constexpr (OUT64) {
+                    double* out = reinterpret_cast<double*>(p.pred) + idx0;
 #pragma unroll 1
-                for (int r = 0; r < p.IX * nyh; ++r) {
-                    const int xo = nyh == 2 ? (r >> 1) : r, yo = nyh == 2 ? ((r & 1) << 5) + lane : lane;
-                    float* a = arow + xo * p.AS + (yo - lane);
-                    const float sf = *a;
-                    *a = 0.f;
-                    const int gx = x0 + xo, gy = y0 + yo;
-                    if (gz >= p.Z || gx >= p.X || gy >= p.Y) continue;
-                    const size_t idx = idx0 + (size_t)xo * p.Y + yo;
-                    double sd = (double)sf;
-                    if (sf != 0.f && fabsf(sf) < eps) {  // within float32 rounding distance of zero: the sign decides the gate
-                        ex.k64 = p.k64 + (MULTI ? (size_t)q * (T + 1) : 0);
-                        sd = exact_sum_f64(ex, b, gz, gx, gy);
+                    for (int xo = 0; xo < p.IX; ++xo, a += p.AS, out += p.Y) {
+                        const float sa = a[0];
+                        a[0] = 0.f;
+                        float sb = 0.f;
+                        if (nyh == 2) { sb = a[32]; a[32] = 0.f; }
+                        if (xo < nrows) {
+                            if (in0) out[0] = sa > 0.f ? tanh_pos_f64_tab((double)sa, tab) : 0.0;
+                            if (in1) out[32] = sb > 0.f ? tanh_pos_f64_tab((double)sb, tab) : 0.0;
+                        }
                     }
-                    if constexpr (OUT64) {
-                        double o = 0.0;
-                        if (sd > 0.0) o = tanh_pos_f64_tab(sd, tab);
-                        reinterpret_cast<double*>(p.pred)[idx] = o;
-                    } else {
-                        const float s32 = (float)sd;
-                        reinterpret_cast<float*>(p.pred)[idx] = sd > 0.0 ? fmaxf(tanhf(s32), 1.401298464e-45f) : 0.f;
+                } else {
+                    float* out = reinterpret_cast<float*>(p.pred) + idx0;
+#pragma unroll 1
+                    for (int xo = 0; xo < p.IX; ++xo, a += p.AS, out += p.Y) {
+                        const float sa = a[0];
+                        a[0] = 0.f;
+                        float sb = 0.f;
+                        if (nyh == 2) { sb = a[32]; a[32] = 0.f; }
+                        if (xo < nrows) {
+                            if (in0) out[0] = sa > 0.f ? tanhf(sa) : 0.f;
+                            if (in1) out[32] = sb > 0.f ? tanhf(sb) : 0.f;
+                        }
                     }
                 }
             }
@@ -718,7 +747,7 @@ static int launch_fs(FsParams& p, size_t smem, size_t smem_occ, cudaStream_t str
 // state: the grid state buffer (NULL: scanning kernel, no mask); gate: whole-grid selection against the dense stencil
 // (NULL: run); handoff: append tiles above the break-even occupancy to the state buffer's tile list instead of
 // scattering them (the caller enqueues the dense stencil's tile-list pass behind this launch)
-int fwd_sparse_launch(const float* x, const float* Kstar, const double* Kstar64, void* pred, int out_f64, unsigned long long* state,
+int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f64, unsigned long long* state,
                       const unsigned long long* gate, unsigned long long nnz_max, unsigned long long dw_max, bool handoff,
                       int B, int Z, int X, int Y, int kz, int kx, int ky, int nq, cudaStream_t stream) {
     FsParams p{};
@@ -727,7 +756,7 @@ int fwd_sparse_launch(const float* x, const float* Kstar, const double* Kstar64,
     if (nq < 1 || !plan_fwd_sparse(B, Z, X, Y, kz, kx, ky, p, smem, ni2, nq, &smem_occ)) return SN_ERR_UNSUPPORTED;
     p.nq = nq;
     p.pred_qstride = (long long)B * Z * X * Y;
-    p.x = x; p.Kstar = Kstar; p.k64 = Kstar64; p.pred = pred; p.out_f64 = out_f64; p.nnz = gate; p.nnz_max = nnz_max; p.dw_max = dw_max;
+    p.x = x; p.Kstar = Kstar; p.pred = pred; p.out_f64 = out_f64; p.nnz = gate; p.nnz_max = nnz_max; p.dw_max = dw_max;
     p.tanh64 = out_f64;  // float64 predictions: tanh evaluated in float64
     {
         static const bool no_mask = SN_ENV("SN_FWD_NO_MASK") != nullptr;  // measurement: force the scanning kernel

@@ -25,14 +25,7 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p, int
                 }
             }
         }
-        if (p.k64 && s != 0.f && fabsf(s) < (float)(__ldg(p.k64 + p.kz * p.kx * ky) * 3.814697265625e-6)) {
-            // within float32 rounding distance of zero: the sign is decided in float64 (stencil_common.cuh)
-            ExactSum ex;
-            ex.x = p.x; ex.k64 = p.k64; ex.Z = p.Z; ex.X = p.X; ex.Y = p.Y; ex.kz = p.kz; ex.kx = p.kx; ex.ky = ky;
-            ex.plz = plz; ex.plx = plx; ex.ply = ply; ex.eps_rel = 0.f;
-            s = (float)exact_sum_f64(ex, (int)b, z, x, y);
-        }
-        const float o = s > 0.f ? fmaxf(tanhf(s), 1.401298464e-45f) : 0.f;
+        const float o = s > 0.f ? tanhf(s) : 0.f;
         if (p.out_f64)
             reinterpret_cast<double*>(p.pred)[i] = (double)o;
         else

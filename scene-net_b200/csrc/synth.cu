@@ -12,6 +12,7 @@
 // Latency-bound by construction (<= 16 operators x <= 4096 taps): one CTA, no roofline.
 #include <math.h>
 #include "common.cuh"
+#include "peer_exchange.cuh"
 
 namespace sn {
 
@@ -147,7 +148,7 @@ __device__ float lambda_eff_of(const SynthArgs& a, int g) {
 // =====================================================================================
 __global__ void __launch_bounds__(kSynthThreads * kSynthGroups, 1)
 synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restrict__ lambda_eff,
-                 float* __restrict__ Kstar, double* __restrict__ Kstar64, float* __restrict__ snapshot, int write_last) {
+                 float* __restrict__ Kstar, float* __restrict__ snapshot, int write_last) {
     extern __shared__ float s_raw_all[];  // [groups][Tp]
     __shared__ float s_off_all[kSynthGroups][64];  // per-slice mean (plane kinds) or [0] = volume offset
     __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
@@ -207,24 +208,10 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restric
         __threadfence_block();
         __syncthreads();  // every operator's kernel is in K now
         if (Kstar) {
-            double l1 = 0.0;
             for (int t = tid; t < T; t += blockDim.x) {
                 double acc = 0.0;  // Kstar = sum_g lambda_eff[g] * K_g, float64, fixed order
                 for (int g = 0; g < a.d.n_geneos; ++g) acc += (double)s_lam[g] * (double)K[(size_t)g * T + t];
                 Kstar[t] = (float)acc;
-                if (Kstar64) Kstar64[t] = acc;
-                l1 += fabs(acc);
-            }
-            if (Kstar64) {  // Kstar64[T] = sum_t |Kstar64[t]|: scale of the forward's near-zero test (fixed-order block sum)
-                __shared__ double s_l1[kSynthThreads * kSynthGroups / 32];
-                l1 = warp_sum(l1);
-                if (lane == 0) s_l1[tid >> 5] = l1;
-                __syncthreads();
-                if (tid == 0) {
-                    double tot = 0.0;
-                    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_l1[w];
-                    Kstar64[T] = tot;
-                }
             }
         }
         if (lambda_eff && tid < a.d.n_geneos) lambda_eff[tid] = s_lam[tid];
@@ -237,11 +224,15 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restric
 // Backward.  MODE 0: dK given [G,T] (double).  MODE 1: dK_g = lambda_eff[g] * W (observer),
 // plus dlambda_g = <K_g - K_last, W>.
 // =====================================================================================
+// MODE 2 = MODE 1 followed by the all-reduce (sum over ranks) of dparams over NVLink peer memory, by this CTA itself
+// (peer_exchange.cuh): the exchange starts the moment the gradients exist — no second launch, no launch gap on the
+// critical path of a multi-GPU step.
 template <int MODE>
 __global__ void __launch_bounds__(kSynthThreads * kSynthGroups, 1)
 synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__ dK, const float* __restrict__ K,
                  const float* __restrict__ lambda_eff, const double* __restrict__ W, double scale,
-                 float* __restrict__ dparams) {
+                 float* __restrict__ dparams, const __grid_constant__ PeerArgs peer) {
+    constexpr bool kObserver = MODE >= 1;
     __shared__ double s_mean_all[kSynthGroups][64];
     __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
     const int kz = a.d.kz, kx = a.d.kx, ky = a.d.ky, P = kx * ky, T = kz * P;
@@ -257,8 +248,8 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
         const int kind = a.d.kind[g];
         const OpParams o = load_op(a, g);
         const bool plane = is_plane_kind(kind);
-        const double lam = MODE == 1 ? (double)lambda_eff[g] : 1.0;
-        auto dk = [&](int t) -> double { return MODE == 1 ? lam * W[t] : dK[(size_t)g * T + t]; };
+        const double lam = kObserver ? (double)lambda_eff[g] : 1.0;
+        auto dk = [&](int t) -> double { return kObserver ? lam * W[t] : dK[(size_t)g * T + t]; };
 
         // projection D = dK - mean(dK) over the zero-sum group (slice or whole volume)
         double vol_mean = 0.0;
@@ -345,7 +336,7 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
             if (tid == 0) dparams[a.d.param_index[g] + k] = (float)(s * scale);
         }
 
-        if (MODE == 1 && a.d.lambda_index[g] >= 0 && g != a.d.last_lambda) {
+        if (kObserver && a.d.lambda_index[g] >= 0 && g != a.d.last_lambda) {
             // dL/dlambda_g = <K_g, W> - <K_last, W>   (SCENE_Net.py:329-335)
             const int last = a.d.last_lambda;
             double s = 0.0;
@@ -358,6 +349,10 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
             if (tid == 0) dparams[a.d.lambda_index[g]] = (float)(s * scale);
         }
         group_sync(group);
+    }
+    if constexpr (MODE == 2) {
+        __syncthreads();  // every group's gradients are in dparams (written by this CTA: visible after the barrier)
+        peer_exchange(peer, dparams, a.d.n_param_ptrs);
     }
 }
 
@@ -391,7 +386,7 @@ static void fill_args(SynthArgs& a, const sn_model_desc* d, const float* const* 
 }  // namespace sn
 
 extern "C" int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const* param_ptrs_host, float* K,
-                                  float* lambda_eff, float* Kstar, double* Kstar64, float* param_snapshot, int write_last_lambda,
+                                  float* lambda_eff, float* Kstar, float* param_snapshot, int write_last_lambda,
                                   void* stream) {
     int rc = sn::check_desc(desc, param_ptrs_host);
     if (rc) return rc;
@@ -405,7 +400,7 @@ extern "C" int sn_geneo_synth_fwd(const sn_model_desc* desc, const float* const*
         cudaError_t e = cudaFuncSetAttribute(sn::synth_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return sn::cuda_rc(e);
     }
-    sn::synth_fwd_kernel<<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, Kstar64, param_snapshot, write_last_lambda);
+    sn::synth_fwd_kernel<<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, K, lambda_eff, Kstar, param_snapshot, write_last_lambda);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -418,7 +413,7 @@ extern "C" int sn_geneo_synth_bwd(const sn_model_desc* desc, const float* const*
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
     const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
-    sn::synth_bwd_kernel<0><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, dK, nullptr, nullptr, nullptr, 1.0, dparams);
+    sn::synth_bwd_kernel<0><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, dK, nullptr, nullptr, nullptr, 1.0, dparams, sn::PeerArgs{});
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -432,7 +427,27 @@ extern "C" int sn_scenenet_param_grads(const sn_model_desc* desc, const float* c
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
     const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
-    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams);
+    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, sn::PeerArgs{});
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
+extern "C" int sn_scenenet_param_grads_allreduce(const sn_model_desc* desc, const float* const* param_ptrs_host, const float* K,
+                                                 const float* lambda_eff, const double* W, double scale, float* dparams,
+                                                 int rank, int world, const uint64_t* peer_bufs_host, uint32_t* seq_counter,
+                                                 int32_t* status, int64_t timeout_ms, void* stream) {
+    int rc = sn::check_desc(desc, param_ptrs_host);
+    if (rc) return rc;
+    if (!K || !lambda_eff || !W || !dparams || desc->lambda_index[0] < 0) return SN_ERR_BAD_ARG;
+    sn::PeerArgs peer;
+    rc = sn::fill_peer_args(peer, rank, world, peer_bufs_host, seq_counter, status, timeout_ms);
+    if (rc) return rc;
+    sn::SynthArgs a;
+    sn::fill_args(a, desc, param_ptrs_host);
+    // the exchange needs one warp per rank: at least 32 * world threads
+    int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
+    while (sn::kSynthThreads * groups < 32 * world) ++groups;
+    sn::synth_bwd_kernel<2><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, peer);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }

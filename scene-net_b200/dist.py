@@ -57,7 +57,14 @@ class PeerAllReduce:
     mappings); the data path is our kernel.  Raises at construction when peer memory is not available (the caller
     then keeps the NCCL all-reduce)."""
 
-    def __init__(self, device, group=None):
+    #: models recognise this and let the parameter-Jacobian kernel do the exchange itself
+    #: (sn_scenenet_param_grads_allreduce: no separate launch on the step's critical path)
+    fused_with_param_grads = True
+
+    def __init__(self, device, group=None, timeout_s: float = 600.0):
+        """timeout_s: bound on the wait for a peer (0 = wait for ever).  Like a collective watchdog, running into it is
+        fatal (the kernel traps and the next CUDA call raises): ranks skew by minutes around checkpoints / validation,
+        so keep it in minutes.  `ok()` / `check()` read the status word at a point of the caller's choosing."""
         import ctypes as C
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -78,6 +85,7 @@ class PeerAllReduce:
         self.ptrs = (C.c_uint64 * self.world)(*ptrs)
         self.seq = torch.zeros(1, dtype=torch.int32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.timeout_ms = int(max(0.0, float(timeout_s)) * 1000)
         self._check, self._lib = check, lib
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's buffer is zeroed and mapped before the first exchange
@@ -89,9 +97,17 @@ class PeerAllReduce:
         from .ops import _on_device, _stream
         with _on_device(flat.device):
             self._check(self._lib.sn_peer_allreduce(flat.data_ptr(), flat.numel(), self.rank, self.world, self.ptrs,
-                                                    self.seq.data_ptr(), self.status.data_ptr(), _stream()), "sn_peer_allreduce")
+                                                    self.seq.data_ptr(), self.status.data_ptr(), self.timeout_ms, _stream()),
+                        "sn_peer_allreduce")
         return flat
 
     def ok(self) -> bool:
-        """False if any call timed out waiting for a peer (device sync)."""
+        """False if any call ran into the bound waiting for a peer (device sync; the kernel has trapped by then, so the
+        synchronisation itself raises on a live failure — this is for post-mortems and tests)."""
         return int(self.status) == 0
+
+    def check(self) -> None:
+        """raise if an exchange failed (call at a safe point, e.g. once per optimizer step or per epoch)"""
+        if not self.ok():
+            raise RuntimeError("scenenet_b200: a peer did not answer the gradient exchange within "
+                               f"{self.timeout_ms / 1000:.0f} s; the replicas are out of step")

@@ -156,36 +156,24 @@ def unused_cone_params(kind: int, hc: int, kz: int, base: int) -> set:
 
 
 # ------------------------------------------------------------------------------- synthesis
-class KstarTensor(torch.Tensor):
-    """Kstar [kz,kx,ky] float32 with its unrounded float64 twin riding along as `.k64` ([T+1]: taps, then sum |tap|;
-    sn_geneo_synth_fwd, ABI v4) — the forward kernels decide the sign of sums near zero with it."""
-    k64: Optional[torch.Tensor] = None
-
-
 def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lambda: bool = False):
-    """-> (K [G,kz,kx,ky] f32, lambda_eff [G] f32 | None, Kstar [kz,kx,ky] f32 | None, snapshot [n] f32); Kstar carries
-    its float64 twin as `Kstar.k64`"""
+    """-> (K [G,kz,kx,ky] f32, lambda_eff [G] f32 | None, Kstar [kz,kx,ky] f32 | None, snapshot [n] f32)"""
     d = spec.desc()
     if len(params) != d.n_param_ptrs:
         raise ValueError(f"expected {d.n_param_ptrs} parameter tensors, got {len(params)}")
     dev = params[0].device
     G, T = len(spec.kinds), spec.taps
-    # one allocation for the five small outputs (views into it): Kstar64 | K | Kstar | lambda_eff | snapshot, each 16-byte aligned
+    # one allocation for the four small outputs (views into it): K | Kstar | lambda_eff | snapshot, each 16-byte aligned
     Tp = (T + 3) & ~3
-    n_64 = (2 * (T + 1) + 3) & ~3 if spec.observer else 0
     n_k, n_ks, n_l, n_s = G * Tp, (Tp if spec.observer else 0), (((G + 3) & ~3) if spec.observer else 0), d.n_param_ptrs
-    buf = torch.empty(n_64 + n_k + n_ks + n_l + n_s, dtype=torch.float32, device=dev)
-    k64 = buf[:2 * (T + 1)].view(torch.float64) if spec.observer else None
-    K = buf[n_64:n_64 + G * T].view(G, *spec.kernel_size)
-    Kstar = buf[n_64 + n_k:n_64 + n_k + T].view(tuple(spec.kernel_size)) if spec.observer else None
-    lam = buf[n_64 + n_k + n_ks:n_64 + n_k + n_ks + G] if spec.observer else None
-    snap = buf[n_64 + n_k + n_ks + n_l:]
+    buf = torch.empty(n_k + n_ks + n_l + n_s, dtype=torch.float32, device=dev)
+    K = buf[:G * T].view(G, *spec.kernel_size)
+    Kstar = buf[n_k:n_k + T].view(tuple(spec.kernel_size)) if spec.observer else None
+    lam = buf[n_k + n_ks:n_k + n_ks + G] if spec.observer else None
+    snap = buf[n_k + n_ks + n_l:]
     with _on_device(dev):
-        check(lib.sn_geneo_synth_fwd(C.byref(d), _ptr_array(params), K.data_ptr(), _ptr(lam), _ptr(Kstar), _ptr(k64),
+        check(lib.sn_geneo_synth_fwd(C.byref(d), _ptr_array(params), K.data_ptr(), _ptr(lam), _ptr(Kstar),
                                      snap.data_ptr(), int(write_last_lambda), _stream()), "sn_geneo_synth_fwd")
-    if Kstar is not None:
-        Kstar = Kstar.as_subclass(KstarTensor)
-        Kstar.k64 = k64
     return K, lam, Kstar, snap
 
 
@@ -202,12 +190,20 @@ def synth_bwd(spec: ObserverSpec, snapshot: torch.Tensor, dK: torch.Tensor) -> t
 
 
 def param_grads(spec: ObserverSpec, snapshot: torch.Tensor, K: torch.Tensor, lambda_eff: torch.Tensor, W: torch.Tensor,
-                scale: float = 1.0) -> torch.Tensor:
+                scale: float = 1.0, peer=None) -> torch.Tensor:
+    """parameter gradients from the tap gradient W; `peer` (a dist.PeerAllReduce): the same launch also sums them over the
+    ranks through NVLink peer memory (sn_scenenet_param_grads_allreduce)"""
     d = spec.desc()
     out = torch.empty(d.n_param_ptrs, dtype=torch.float32, device=W.device)
     with _on_device(W.device):
-        check(lib.sn_scenenet_param_grads(C.byref(d), _snapshot_ptr_array(snapshot), K.data_ptr(), lambda_eff.data_ptr(),
-                                          W.data_ptr(), float(scale), out.data_ptr(), _stream()), "sn_scenenet_param_grads")
+        if peer is None:
+            check(lib.sn_scenenet_param_grads(C.byref(d), _snapshot_ptr_array(snapshot), K.data_ptr(), lambda_eff.data_ptr(),
+                                              W.data_ptr(), float(scale), out.data_ptr(), _stream()), "sn_scenenet_param_grads")
+        else:
+            check(lib.sn_scenenet_param_grads_allreduce(C.byref(d), _snapshot_ptr_array(snapshot), K.data_ptr(), lambda_eff.data_ptr(),
+                                                        W.data_ptr(), float(scale), out.data_ptr(), peer.rank, peer.world, peer.ptrs,
+                                                        peer.seq.data_ptr(), peer.status.data_ptr(), peer.timeout_ms, _stream()),
+                  "sn_scenenet_param_grads_allreduce")
     return out
 
 
@@ -289,15 +285,14 @@ def scenenet_fwd(x32: torch.Tensor, Kstar: torch.Tensor, out_dtype: torch.dtype,
     pred = torch.empty(x32.shape, dtype=out_dtype, device=x32.device)
     if x32.numel() == 0:
         return pred
-    k64 = getattr(Kstar, "k64", None)  # float64 taps from synth_fwd: sign of sums near zero decided in float64
     with _on_device(x32.device):
-        check(lib.sn_scenenet_fwd(x32.data_ptr(), _ptr(nnz), int(mode), Kstar.data_ptr(), _ptr(k64), B, Z, X, Y, kz, kx, ky,
-                                  pred.data_ptr(), _DT[out_dtype], _stream()), "sn_scenenet_fwd")
+        check(lib.sn_scenenet_fwd(x32.data_ptr(), _ptr(nnz), int(mode), Kstar.data_ptr(), B, Z, X, Y, kz, kx, ky, pred.data_ptr(),
+                                  _DT[out_dtype], _stream()), "sn_scenenet_fwd")
     return pred
 
 
 def scenenet_fwd_multi(x32: torch.Tensor, Kstars: torch.Tensor, out_dtype: torch.dtype, nnz: Optional[torch.Tensor] = None,
-                       mode: int = 0, k64s: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       mode: int = 0) -> torch.Tensor:
     """several observers on the same grids (SCENENetQuantile): Kstars [Q,kz,kx,ky] float32 -> preds [Q,B,1,Z,X,Y];
     with the grid state `nnz` the occupancy-driven kernel lists the non-zero voxels once for all Q tap sets."""
     _need_cuda(x32, "x")
@@ -309,12 +304,8 @@ def scenenet_fwd_multi(x32: torch.Tensor, Kstars: torch.Tensor, out_dtype: torch
     preds = torch.empty((Q, *x32.shape), dtype=out_dtype, device=x32.device)
     if x32.numel() == 0:
         return preds
-    if k64s is not None:
-        if k64s.dtype != torch.float64 or tuple(k64s.shape) != (Q, kz * kx * ky + 1):
-            raise TypeError("k64s must be float64 [Q, T + 1] (the Kstar.k64 of every observer)")
-        k64s = k64s.contiguous()
     with _on_device(x32.device):
-        check(lib.sn_scenenet_fwd_multi(x32.data_ptr(), _ptr(nnz), int(mode), Kstars.data_ptr(), _ptr(k64s), Q, B, Z, X, Y, kz, kx, ky,
+        check(lib.sn_scenenet_fwd_multi(x32.data_ptr(), _ptr(nnz), int(mode), Kstars.data_ptr(), Q, B, Z, X, Y, kz, kx, ky,
                                         preds.data_ptr(), _DT[out_dtype], _stream()), "sn_scenenet_fwd_multi")
     return preds
 

@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     """error paths return codes before any CUDA call"""
     from scenenet_b200._lib import lib
-    assert lib.sn_scenenet_fwd(None, None, 0, None, None, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
-    assert lib.sn_scenenet_fwd_multi(None, None, 0, None, None, 3, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
+    assert lib.sn_scenenet_fwd(None, None, 0, None, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
+    assert lib.sn_scenenet_fwd_multi(None, None, 0, None, 3, 1, 8, 8, 8, 3, 3, 3, None, 0, None) == -1
     assert lib.sn_cast_f64_to_f32(None, None, 4, None) == -1
     assert lib.sn_threshold(None, 0, 0.5, 4, None, None) == -1
     assert lib.sn_scenenet_bwd_workspace_bytes(0, 8, 8, 8, 3, 3, 3) == -1
@@ -45,7 +45,8 @@ def test_argument_validation_without_gpu():
     assert lib.sn_criterion_fwd(None, None, 1, 8, None, None, 10, 1.0, 2.0, 1.0, 4.0, 1e-6, 3, None, None, None, 0, None) == -1
     assert lib.sn_param_penalty(None, None, 0, 5.0, None, None, None) == -1
     assert lib.sn_peer_allreduce_buffer_bytes(8) == 2 * 8 * 128 * 4 and lib.sn_peer_allreduce_buffer_bytes(17) == -1
-    assert lib.sn_peer_allreduce(None, 13, 0, 2, None, None, None, None) == -1
+    assert lib.sn_peer_allreduce(None, 13, 0, 2, None, None, None, 1000, None) == -1
+    assert lib.sn_scenenet_param_grads_allreduce(None, None, None, None, None, 1.0, None, 0, 2, None, None, None, 1000, None) == -1
     # the selection rule of the AUTO modes (host-side query): config 2 at 1.6 % -> occupancy-driven forward and backward
     n = int(0.016 * 32 * 64 ** 3)
     assert lib.sn_select_path(0, n, 32, 64, 64, 64, 9, 5, 5) == 2 and lib.sn_select_path(1, n, 32, 64, 64, 64, 9, 5, 5) == 2

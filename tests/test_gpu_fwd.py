@@ -67,9 +67,10 @@ def test_sparse_and_dense_forward_match_float64_reference(B, grid, ks, density, 
     assert torch.equal(ps, ops.scenenet_fwd(x, K, out_dtype, mode=SN_PATH_SPARSE)), "deterministic"
 
 
-@pytest.mark.parametrize("density,expect_sparse", [(0.005, True), (0.016, True), (0.045, False), (1.0, False)])
+@pytest.mark.parametrize("density,expect_sparse", [(0.005, True), (0.016, True), (0.045, True), (0.3, False), (1.0, False)])
 def test_device_side_selection(density, expect_sparse):
-    """AUTO + the count from sn_grid_prepare picks the kernel on the device (threshold for a 5 x 5 slice: 3 % occupancy)."""
+    """AUTO + the state buffer of sn_grid_prepare: the kernel is chosen per tile on the device (ABI v4; a tile goes to the
+    dense stencil when its halo box is more than ~10 % occupied) — uniform grids get one kernel for all tiles."""
     from scenenet_b200 import ops
     from scenenet_b200._lib import SN_PATH_AUTO, SN_PATH_DENSE, SN_PATH_SPARSE
     ks = (9, 5, 5)

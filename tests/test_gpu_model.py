@@ -62,7 +62,9 @@ def test_kernel_synthesis_and_jacobian_vs_reference(golden_dir):
         # evaluated in float64 (oracle synthesis on float64 parameters = the exact kernel) against the reference's float32
         # output (K = raw - mean(raw): a nearly flat slice is the difference of numbers ~sigma and carries ~1e-7 of noise)
         p64 = {k: torch.tensor(float(ps[k]), dtype=torch.float64, requires_grad=(k != "apex")) for k in names}
-        K64 = mo.SYNTH[cname](p64, ks)
+        with mo.exact_arithmetic():
+            K64 = mo.SYNTH[cname](p64, ks)
+        assert K64.dtype == torch.float64
         ref_noise = float(np.abs(Kref - K64.detach().numpy()).max())
         tol = 1e-6 * np.abs(Kref).max() + 2.0 * ref_noise
         err = float(np.abs(K.detach().cpu().numpy() - Kref).max())

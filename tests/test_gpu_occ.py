@@ -136,11 +136,21 @@ def test_quantile_model_one_forward_for_all_observers(case):
         x = (torch.rand(shape, generator=g, device=DEV) < (0.3 if case == "dense" else 0.02)).double()
     if case == "float32":
         x = x.float()
-    per_net = qnet(x)                       # gradients enabled: one observer after the other
-    with torch.no_grad():
-        fused = qnet(x)
+    qnet.per_observer_forward = True        # the reference's loop: one observer after the other
+    per_net = qnet(x)
+    per_net.square().sum().backward()
+    g_ref = [None if p.grad is None else p.grad.clone() for p in qnet.parameters()]
+    for p in qnet.parameters():
+        p.grad = None
+    qnet.per_observer_forward = False       # one forward launch for all observers, one autograd node
+    fused = qnet(x)
     assert fused.shape == per_net.shape == (2, 3, 32, 32, 64) and fused.dtype == torch.float32
-    assert torch.equal(fused, per_net.detach())
+    assert torch.equal(fused.detach(), per_net.detach())
+    fused.square().sum().backward()         # training through the fused forward: identical gradients
+    for p, r in zip(qnet.parameters(), g_ref):
+        assert (p.grad is None) == (r is None) and (r is None or torch.equal(p.grad, r))
+    with torch.no_grad():
+        assert torch.equal(qnet(x), fused.detach())
     # the entry point itself, every mode, against single-observer launches
     x32, st = ops.prepare(x)
     Ks = torch.randn((3, 9, 5, 5), generator=g, device=DEV) * 0.2

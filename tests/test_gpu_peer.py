@@ -77,3 +77,77 @@ def test_peer_allreduce_matches_nccl():
     if any(r[1] == "unavailable" for r in res):
         pytest.skip(f"peer memory unavailable: {res}")
     assert all(r[1] == "ok" for r in res), res
+
+
+def _ddp_worker(rank, world, port, q):
+    """each rank: its shard of the batch through SceneNet with the fused Jacobian + exchange kernel
+    (sn_scenenet_param_grads_allreduce); the result must be the MEAN of the per-shard gradients (Lightning's implicit DDP
+    for the reference, scripts/main.py:224-236) — checked against the per-shard oracle gradients computed on the host"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import scenenet_b200 as sb
+    from oracle import model_oracle as mo, ref_shim
+    from scenenet_b200 import dist as sdist
+    r, w, dev = sdist.init_from_env()
+    try:
+        ar = sdist.PeerAllReduce(dev, timeout_s=120)
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "unavailable", f"{type(e).__name__}: {e}"))
+        return
+    B = 4  # global batch: 2 grids per rank
+    x, y = mo.synthetic_grids(B, (32, 32, 32), seed=31, p_gt=2e-3)
+    lo, hi = sdist.shard_range(B, rank, world)
+    torch.manual_seed(0)
+    m = sb.SceneNet(dict(mo.KAT_GENEO_NUM), (9, 5, 5)).to(dev)
+    ref_shim.set_scenenet_params(m, mo.KAT_PARAMS, mo.KAT_LAMBDAS, mo.KAT_LAST)
+    m.grad_scale = 1.0 / world
+    m.grad_sync_group = ar
+    pred = m(x[lo:hi].to(dev))
+    loss = mo.geneo_tversky_criterion(pred, y[lo:hi].to(dev), m.get_cvx_coefficients(), m.last_lambda, list(m.get_geneo_params().values()))
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: (None if p.grad is None else float(p.grad)) for n, p in m.named_parameters()}
+    # oracle: every shard on the host, then the mean
+    shards = []
+    for rr in range(world):
+        a, b = sdist.shard_range(B, rr, world)
+        _, _, g = mo.fwd_bwd(mo.kat_model(), x[a:b], y[a:b])
+        shards.append(g)
+    bad = []
+    for n, v in shards[0].items():
+        if v is None:
+            if got[n] is not None:
+                bad.append((n, got[n], None))
+            continue
+        mean = sum(s[n] for s in shards) / world
+        # the criterion's penalty terms act on the live parameters outside our autograd node: every rank adds the full
+        # (not 1/world-scaled, not exchanged) penalty gradient, as under DDP where they are averaged over identical replicas;
+        # the KAT parameters are all positive, so those terms are zero here
+        if abs(got[n] - mean) > 1e-5 * abs(mean) + 1e-9:
+            bad.append((n, got[n], mean))
+    ok = not bad and ar.ok()
+    # all ranks hold the same bits
+    flat = torch.tensor([0.0 if v is None else v for v in got.values()], device=dev, dtype=torch.float64)
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    ok = ok and all(torch.equal(o, other[0]) for o in other)
+    dist.barrier()
+    q.put((rank, "ok" if ok else "mismatch", repr(bad[:3])))
+
+
+def test_ddp_semantics_mean_of_per_shard_oracle_gradients():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    if any(r[1] == "unavailable" for r in res):
+        pytest.skip(f"peer memory unavailable: {res}")
+    assert all(r[1] == "ok" for r in res), res

@@ -35,11 +35,11 @@ def _x575(golden_dir):
     return torch.from_numpy(x).view(1, 1, 64, 64, 64), torch.from_numpy(y).view(1, 1, 64, 64, 64)
 
 
-def _check_grads(got, ref, rtol=RTOL, ref_other=None):
-    """each gradient within 1e-5 relative of the reference's.  `ref_other`: the same step run by the reference on another
-    device (its own CUDA path): a gradient the reference itself cannot reproduce better than that between its two
-    devices (tiny, cancellation-dominated entries) is held to twice that measured spread instead, capped at 1e-6 of the
-    largest gradient"""
+def _check_grads(got, ref, rtol=RTOL):
+    """each gradient within 1e-5 relative of the reference's.  The 11 gradients of one backward are reductions over the same
+    tap gradient; an entry that is tiny because its terms cancel (e.g. neg_factor: 5.8e-4 next to 0.26) cannot be resolved
+    below one float32 ulp of the LARGEST gradient by any float32 path: such entries are held to 1e-7 * max |gradient|
+    (round 1 allowed 2e-6 * max here)."""
     worst = 0.0
     gmax = max(abs(v) for v in ref.values() if v is not None)
     for n, r in ref.items():
@@ -49,9 +49,8 @@ def _check_grads(got, ref, rtol=RTOL, ref_other=None):
         assert got[n] is not None, n
         err = abs(got[n] - r)
         rel = err / max(abs(r), 1e-30)
-        slack = 0.0 if ref_other is None else min(2.0 * abs(ref_other[n] - r), 1e-6 * gmax)
-        worst = max(worst, rel if err > slack else 0.0)
-        assert rel <= rtol or err <= max(slack, 1e-12), (n, got[n], r, rel, slack)
+        worst = max(worst, rel if err > 1e-7 * gmax else 0.0)
+        assert rel <= rtol or err <= 1e-7 * gmax, (n, got[n], r, rel, gmax)
     return worst
 
 
@@ -84,10 +83,10 @@ def test_reference_criterion_class_runs_unchanged_on_cuda_model(golden_dir, case
     err = np.abs(pred.cpu().numpy() - ref).max()
     assert err <= RTOL * np.abs(ref).max(), (err, np.abs(ref).max())
     assert abs(loss - meta["loss"]) <= RTOL * abs(meta["loss"]), (loss, meta["loss"])
-    # the reference on its own CUDA path: how well it reproduces its own CPU gradients
+    # for the record: how well the reference reproduces its own CPU gradients on its own CUDA path
     _, _, g_ref_gpu, _ = ref_runner.criterion_step(x, y, mo.KAT_GENEO_NUM, ks, params, lambdas, last, device=DEV)
-    spread = max(abs(g_ref_gpu[n] - r) / abs(r) for n, r in meta["grads"].items() if r is not None)
-    worst = _check_grads(grads, meta["grads"], ref_other=g_ref_gpu)
+    spread = max(abs(g_ref_gpu[n] - r) / abs(r) for n, r in meta["grads"].items() if r)
+    worst = _check_grads(grads, meta["grads"])
     print(f"{case}: reference GENEO_Tversky_Loss over the CUDA model: loss rel {abs(loss - meta['loss']) / abs(meta['loss']):.2e}, "
           f"worst grad rel {worst:.2e} (the reference's own CPU-vs-CUDA spread: {spread:.2e})")
 
