@@ -37,14 +37,14 @@ L2_BYTES = 126 * 1024 * 1024
 
 
 # ----------------------------------------------------------------------------------------------
-def kat_model(device):
+def kat_model(device, kernel=None):
     """SceneNet({'cy':1,'cone':1,'neg':1}, (9,5,5)) with the SURVEY §8c parameter vector."""
     import scenenet_b200 as sb
     params = {"cy_0.radius": 2.5, "cy_0.sigma": 1.8, "cone_0.apex": 4.0, "cone_0.cone_inc": 0.3, "cone_0.cone_radius": 2.0,
               "cone_0.radius": 3.0, "cone_0.sigma": 1.4, "neg_0.neg_factor": 0.2, "neg_0.radius": 8.0, "neg_0.sigma": 0.8}
     lambdas = {"lambda_cone_0": 0.3, "lambda_cy_0": 0.45, "lambda_neg_0": 0.25}
     torch.manual_seed(0)
-    m = sb.SceneNet({'cy': 1, 'cone': 1, 'neg': 1}, KERNEL).to(device)
+    m = sb.SceneNet({'cy': 1, 'cone': 1, 'neg': 1}, tuple(kernel or KERNEL)).to(device)
     with torch.no_grad():
         for name, layer in m.geneos.items():
             for pn, p in layer.geneo_params.items():
@@ -300,6 +300,15 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- config 5
 def run_config5(args):
+    rec = measure_config5(args.steps, args.warmup)
+    if rec is not None:
+        print(json.dumps(rec))
+    sys.stdout.flush()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os._exit(0)
+
+
+def measure_config5(steps, warmup):
     """BASELINE config 5: SemanticKITTI-shaped synthetic scans (~120 k points, float64 rows x,y,z,label; ring pattern
     in +-50 m, z in [-3, 3], pole label 80 kept) -> voxelize to (64, 64, 256) -> SceneNet inference -> threshold 0.65.
     One rank per GPU, SCANS scans per step per GPU; e2e includes the H2D copy of the points and the D2H of the
@@ -355,7 +364,7 @@ def run_config5(args):
         if world > 1:
             dist.barrier()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         graphs[i % 2].replay()
     torch.cuda.synchronize()
     barrier()
@@ -364,7 +373,7 @@ def run_config5(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         graphs[i % 2].replay()
     e1.record()
     torch.cuda.synchronize()
@@ -373,10 +382,10 @@ def run_config5(args):
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    value = SCANS * world * args.steps / (float(ms) * 1e-3)
+    value = SCANS * world * steps / (float(ms) * 1e-3)
     # e2e: points from pinned host memory every step, per-scan counts back to the host
     t0 = time.perf_counter()
-    n_e2e = max(3, min(args.steps, 20))
+    n_e2e = max(3, min(steps, 20))
     for i in range(n_e2e):
         j = i % 2
         dev_rows[j].copy_(host[j], non_blocking=True)
@@ -388,19 +397,55 @@ def run_config5(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = SCANS * world * n_e2e / float(dt)
     if rank == 0:
-        print(json.dumps({
+        return ({
             "metric": "scans/s (voxelize + GENEO inference, KITTI-shaped)", "value": value, "unit": "scans/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms) / args.steps, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": float(ms) / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{SCANS} SemanticKITTI-shaped scans x {NPTS} points per GPU -> (64,64,256) occupancy grids -> "
                                    "SceneNet (9,5,5) forward -> threshold 0.65 (BASELINE config 5)", "parallelism": f"dp{world}",
                        "launch": "CUDA-graph replay"},
             "Mpts_per_s": value * NPTS / 1e6,
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": host[0].numel() * 8, "d2h_bytes_per_step": SCANS * 8},
-            "positive_voxels_first_scan": int(outs[0][0]), "clocks": clocks}))
-    sys.stdout.flush()
+            "positive_voxels_first_scan": int(outs[0][0]), "clocks": clocks})
+    return None
+
+
+def measure_config4(device, rank, world, sync_group, kernel=9, steps=10, warmup=3, batch=8):
+    """BASELINE config 4 in short: 128^3 grids, cubic kernel^3 GENEO kernels, `batch` grids per GPU, fwd + bwd with a fixed
+    upstream gradient, the parameter gradients summed over the ranks inside backward (weak scaling).  CUDA-graph replay."""
+    import torch.distributed as dist
+    from scenenet_b200.graphs import GraphedStep
+    model = kat_model(device, (kernel,) * 3)
+    model.grad_scale = 1.0 / world
+    model.grad_sync_group = sync_group
+    pool = []
+    for s_ in range(2):
+        g = torch.Generator(device=device).manual_seed(1234 + 1000 * rank + s_)
+        x = (torch.rand((batch, 1, 128, 128, 128), generator=g, device=device) < P_OCC).to(torch.float64)
+        dp = torch.randn((batch, 1, 128, 128, 128), generator=g, device=device, dtype=torch.float32).to(torch.float64)
+        pool.append((x, dp))
+    graphs = [GraphedStep(model, x, dpred=dp, specialize=True) for x, dp in pool]
+    for i in range(warmup):
+        graphs[i % 2].replay()
+    torch.cuda.synchronize()
     if world > 1:
-        os._exit(0)
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        graphs[i % 2].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del graphs, pool
+    return {"metric": f"voxel grids/s (128^3 GENEO fwd+bwd, {kernel}^3 kernels)", "value": batch * world * steps / (float(ms) * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_step": float(ms) / steps, "scaling": "weak",
+            "config": {"workload": f"batch {batch} per GPU of synthetic 128^3 occupancy grids (Bernoulli {P_OCC}), kernel ({kernel},)*3, G=3 "
+                                   "(BASELINE config 4)", "parallelism": f"dp{world}"}}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -419,6 +464,7 @@ def main():
                     help="config2 = the headline (default); config4 = 128^3 grids, cubic kernel --kernel, batch 8 per GPU; "
                          "config5 = KITTI-shaped scans: voxelize + GENEO inference")
     ap.add_argument("--kernel", type=int, default=9, help="config4: cubic kernel extent (9, 11, 13, 15)")
+    ap.add_argument("--no-sub-records", action="store_true", help="N > 1: do not add the short config 4 / config 5 records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -451,7 +497,8 @@ def main():
             if os.environ.get("SN_BENCH_NCCL"):
                 raise RuntimeError("forced by SN_BENCH_NCCL")
             model.grad_sync_group = sdist.PeerAllReduce(device)
-            grad_allreduce = "sn_peer_allreduce (one kernel over NVLink peer memory)"
+            grad_allreduce = ("exchange over NVLink peer memory fused into the parameter-Jacobian kernel "
+                              "(sn_scenenet_param_grads_allreduce: no separate collective launch)")
         except Exception as e:  # noqa: BLE001
             model.grad_sync_group = True
             grad_allreduce = f"ncclAllReduce (peer memory unavailable: {type(e).__name__}: {str(e)[:80]})"
@@ -518,9 +565,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms)
     value = B_PER_GPU * world * args.steps / (total_ms * 1e-3)
-    # synth, prepare (cast + non-zero count), forward, g0, tap gradient (its last CTA sums the rows), param_grads
-    # [+ the peer-memory all-reduce kernel]; specialised capture: no gated-out launches
-    kernels_per_step = 6 + (1 if (world > 1 and callable(model.grad_sync_group)) else 0)
+    # synth, prepare (cast + non-zero count + occupancy bits), forward, g0, tap gradient (its last CTA sums the rows),
+    # param_grads (which also exchanges the gradients over NVLink when N > 1); specialised capture: no gated-out launches
+    kernels_per_step = 6 + (1 if (world > 1 and not getattr(model.grad_sync_group, "fused_with_param_grads", False)) else 0)
     if graphs is not None:
         launches = kernels_per_step * args.steps  # replayed graph nodes: the library's host-side counter does not see them
 
@@ -684,6 +731,19 @@ def main():
             torch.cuda.synchronize()
             grad_sync_ok = grad_sync_ok and bool(torch.allclose(probe, ref, rtol=1e-6, atol=0))
     barrier()
+    # BASELINE configs 4 and 5 in short next to the headline whenever several GPUs are used (so that the driver's scaling
+    # runs record them at every N): a few steps each, all ranks take part
+    sub_records = None
+    if world > 1 and args.workload == "config2" and not args.no_sub_records:
+        sub_records = {}
+        for name, fn in (("config4_9^3", lambda: measure_config4(device, rank, world, model.grad_sync_group, 9)),
+                         ("config4_15^3", lambda: measure_config4(device, rank, world, model.grad_sync_group, 15, steps=4, warmup=2)),
+                         ("config5", lambda: measure_config5(10, 3))):
+            try:
+                sub_records[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                sub_records[name] = {"error": repr(e)[:200]}
+            barrier()
     if world > 1 and rank != 0:
         sys.stdout.flush()
         os._exit(0)  # ranks > 0 are done: the remaining sections are rank-0-only and use no collective
@@ -704,16 +764,42 @@ def main():
         reps = 20
 
         def time_kernel(fn):
+            """average duration of one call of fn (one kernel of this library), CUDA events on the launching stream around
+            replays of a CUDA graph that holds one call per input set (no host gaps between the launches: the eager loop
+            used in round 1 was host-bound below ~30 us); inputs rotate over the > L2 pool"""
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(reps):
-                fn(i)
-            b.record()
-            b.synchronize()
-            return a.elapsed_time(b) / reps * 1e-3
+            try:
+                s_ = torch.cuda.Stream(device=device)
+                s_.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(s_):
+                    fn(0)
+                torch.cuda.current_stream(device).wait_stream(s_)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    keep = [fn(i) for i in range(n_sets)]
+                gr.replay()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nrep = max(2, reps // n_sets)
+                a.record()
+                for _ in range(nrep):
+                    gr.replay()
+                b.record()
+                b.synchronize()
+                del keep
+                return a.elapsed_time(b) / (nrep * n_sets) * 1e-3
+            except Exception:  # noqa: BLE001  (capture unavailable: eager loop)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(reps):
+                    fn(i)
+                b.record()
+                b.synchronize()
+                return a.elapsed_time(b) / reps * 1e-3
 
         g0s = [ops.g0(preds[i], pool[i][1]) for i in range(n_sets)]
         from scenenet_b200._lib import SN_PATH_DENSE, SN_PATH_SPARSE
@@ -765,8 +851,10 @@ def main():
             "fwd_occupancy_driven": {"us": None if t_fwd_sp is None else t_fwd_sp * 1e6, "us_auto_selected": t_fwd_auto * 1e6,
                                      "GBps": None if t_fwd_sp is None else bytes_fwd / t_fwd_sp / 1e9,
                                      "hbm_frac": None if t_fwd_sp is None else bytes_fwd / t_fwd_sp / 1e9 / hbm_gbs,
-                                     "note": "non-zero voxels listed from sn_grid_prepare's occupancy bits, scattered into shared-memory "
-                                             "planes; selected on the device below 3 % occupancy (<= 64 taps per slice), 4 % above"},
+                                     "note": "non-zero voxels listed from sn_grid_prepare's occupancy bits (one block-wide scan per tile), "
+                                             "scattered into shared-memory planes, table-driven float64 tanh; us_auto_selected = the "
+                                             "per-tile choice (ABI v4: tiles above ~5.5 % occupancy go to the dense stencil's tile-list "
+                                             "pass, which finds nothing to do on these uniform grids)"},
             "bwd_tapgrad_dense": {"us": t_tap * 1e6, "tflops": fl / t_tap / 1e12, "frac": fl / t_tap / 1e12 / peak_tf},
             "bwd_tapgrad_occupancy_driven": {"us": t_tap_sp * 1e6, "us_auto_selected": t_tap_auto * 1e6, "bound": "hbm",
                                              "GBps": V * 8 / t_tap_sp / 1e9, "hbm_frac": V * 8 / t_tap_sp / 1e9 / hbm_gbs,
@@ -814,6 +902,7 @@ def main():
                     "note": "x (module-boundary dtype) from pinned host memory every step, double-buffered on a copy stream; "
                             "dL/dpred resident on the device (config 2(i)); gradients copied back and read by the host every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "training_step": train_value, "voxelize": vox, "grad_sync_ok": grad_sync_ok,
+            "other_configs": sub_records,
         }
         print(json.dumps(line))
     sys.stdout.flush()
@@ -825,9 +914,9 @@ def main():
 
 def _ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture
-    (profiles/r1b_traffic.json), or None"""
+    (profiles/r2_traffic.json), or None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             d = json.load(f)[kernel]
         return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
     except Exception:  # noqa: BLE001

@@ -141,8 +141,9 @@ class TS40KDeviceLoader:
             raise RuntimeError("TS40KDeviceLoader voxelizes on the GPU: there is no CPU path")
         self.dtype, self.shuffle, self.drop_last = dtype, shuffle, drop_last
         self._rng = random.Random(seed)
-        # staging is a host memcpy / file read per sample: one thread per core up to 16 (8 threads left it at half the PCIe rate)
-        self._pool = ThreadPoolExecutor(max_workers=max(1, io_threads if io_threads else min(16, os.cpu_count() or 8)))
+        # staging is a host memcpy / file read per sample (8 threads; 16 on the 16-core GPU boxes starved the thread that
+        # launches the voxelization and measured 2.5 x slower)
+        self._pool = ThreadPoolExecutor(max_workers=max(1, io_threads if io_threads else min(8, os.cpu_count() or 8)))
         self._staging = [None, None]  # two pinned [cap, 4] float64 buffers, reused across batches
         self._uploaded = [None, None]  # the event of the last H2D copy that READ each pinned slot
         self._copy_stream = torch.cuda.Stream(device=self.device)

@@ -167,9 +167,10 @@ __constant__ double kExp2Tab[64] = {
     1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-__device__ __forceinline__ double tanh_pos_f64_tab(double s, const double* __restrict__ tab) {
-    s = fmin(s, 20.0);  // s > 0 (caller); tanh(20) == 1 to the last bit
-    const double x = -2.0 * s;
+// (takes the float32 sum: the clamp to [0, 20] — tanh(20) == 1 to the last bit, negative sums give exactly 0 — is one
+// float32 instruction instead of a float64 compare + selects; branch-free, so that two calls interleave their DFMA chains)
+__device__ __forceinline__ double tanh_pos_f64_tab(float sf, const double* __restrict__ tab) {
+    const double x = -2.0 * (double)fminf(fmaxf(sf, 0.f), 20.f);
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);  // + 1.5 * 2^52: the low word is rint(x * 64/ln2)
     const int n = __double2loint(t);                                  // in [-3694, 0]
     const double nf = t - 6755399441055744.0;

@@ -296,6 +296,9 @@ fwd_sparse_kernel(const FsParams p) {
 //   straggler), empty tiles are zero-filled with 16-byte stores, and a tile whose halo holds more than `dense_thresh`
 //   non-zeros is appended to the tile list for the dense stencil that follows on the stream (per-TILE kernel choice:
 //   clustered LiDAR grids get the scatter for their sparse tiles and the FFMA stencil for the ground layer).
+#ifndef SN_FO_CTAS
+#define SN_FO_CTAS 4  // resident CTAs per SM for <= 32 taps per slice: 62 registers, no spills, 49 us at config 2; 5 CTAs (48 registers, 104 bytes of spills) measured 55 us (profiles/r2_notes.md)
+#endif
 constexpr int kFoMaxCells = 6;    // cells per thread: HZ * HX * ceil((IY + ky - 1) / 32) <= 1536
 constexpr int kFoCap = 1536;      // list entries per round (incl. the <= HZ padding entries)
 
@@ -319,7 +322,7 @@ __device__ __forceinline__ void fo_rmw(uint32_t addr, float v, float k, int ok) 
 #endif
 
 template <int NI2, bool OUT64, bool MULTI, int CPT>  // CPT: cells per thread this instantiation holds (3 or kFoMaxCells)
-__global__ void __launch_bounds__(kFsThreads, NI2 == 1 ? 5 : (NI2 == 2 ? 4 : 3))
+__global__ void __launch_bounds__(kFsThreads, NI2 == 1 ? SN_FO_CTAS : (NI2 == 2 ? 4 : 3))
 fwd_occ_kernel(const FsParams p) {
     const int nq = MULTI ? p.nq : 1;  // compile-time 1 for the single-observer instantiation: its q loop folds away
     if (p.nnz && !fwd_sparse_selected(p.nnz, p.nnz_max, p.dw_max)) return;  // whole-grid gate (shapes without tile hand-off)
@@ -568,7 +571,7 @@ fwd_occ_kernel(const FsParams p) {
                             // under the PTX memory model
                             const float kk = okp[0] ? skl[q * T + dz * P] : 0.f;
                             asm volatile(
-                                "{\n\t.reg .pred q, more;\n\t.reg .f32 v0, v1, t;\n\t.reg .b32 b0, b1, a;\n\t"
+                                "{\n\t.reg .pred q, more;\n\t.reg .f32 v0, v1, t, u;\n\t.reg .b32 b0, b1, a;\n\t"
                                 "setp.ne.s32 q, %3, 0;\n\t"
                                 "mov.u32 a, %0;\n\t"
                                 "FO_PAIR:\n\t"
@@ -581,9 +584,9 @@ fwd_occ_kernel(const FsParams p) {
                                 "@q fma.rn.f32 t, v0, %4, t;\n\t"
                                 "@q st.shared.f32 [b0], t;\n\t"
                                 FO_ORDER_PTX
-                                "@q ld.shared.f32 t, [b1];\n\t"
-                                "@q fma.rn.f32 t, v1, %4, t;\n\t"
-                                "@q st.shared.f32 [b1], t;\n\t"
+                                "@q ld.shared.f32 u, [b1];\n\t"
+                                "@q fma.rn.f32 u, v1, %4, u;\n\t"
+                                "@q st.shared.f32 [b1], u;\n\t"
                                 FO_ORDER_PTX
                                 "@more bra FO_PAIR;\n\t}" ::"r"(la),
                                 "r"(lend), "r"(accl[0]), "r"(okp[0]), "f"(kk)
@@ -628,9 +631,10 @@ fwd_occ_kernel(const FsParams p) {
                         a[0] = 0.f;
                         float sb = 0.f;
                         if (nyh == 2) { sb = a[32]; a[32] = 0.f; }
-                        if (xo < nrows) {
-                            if (in0) out[0] = sa > 0.f ? tanh_pos_f64_tab((double)sa, tab) : 0.0;
-                            if (in1) out[32] = sb > 0.f ? tanh_pos_f64_tab((double)sb, tab) : 0.0;
+                        if (xo < nrows) {  // warp-uniform
+                            const double oa = tanh_pos_f64_tab(sa, tab), ob = tanh_pos_f64_tab(sb, tab);  // relu inside
+                            if (in0) out[0] = oa;
+                            if (in1) out[32] = ob;
                         }
                     }
                 } else {
@@ -735,7 +739,7 @@ static int launch_fs(FsParams& p, size_t smem, size_t smem_occ, cudaStream_t str
     if (smem > 227 * 1024) return SN_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    const int cap_sm = occ ? (NI2 == 1 ? 5 : (NI2 == 2 ? 4 : 3)) : 4;
+    const int cap_sm = occ ? (NI2 == 1 ? SN_FO_CTAS : (NI2 == 2 ? 4 : 3)) : 4;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > cap_sm ? cap_sm : per_sm);
     const int grid = max(1, min(p.ntiles, kNumSMs * per_sm));
@@ -768,11 +772,12 @@ int fwd_sparse_launch(const float* x, const float* Kstar, void* pred, int out_f6
         p.dense_list = nullptr;
         if (p.state && handoff && (long long)p.ntiles <= state_tile_cap(nvox)) {
             p.dense_list = reinterpret_cast<int*>(const_cast<unsigned*>(p.mask) + state_mask_words(nvox));
-            // break-even of the scatter against the dense stencil, per tile: the scatter costs ~20 scheduler cycles per
-            // (non-zero voxel of the halo box, output plane) pair, the stencil kz * kx * ky / 32 FFMA issue slots per
-            // output voxel; measured crossing at ~10 % occupancy of the box for (9,5,5) (profiles/r2_notes.md)
+            // break-even of the scatter against the dense stencil, per tile: measured on uniform grids (CUDA-graph replay,
+            // (9,5,5), float64 predictions): scatter 49 / 67 / 92 / 131 us at 1.6 / 3 / 5 / 8 % against 95.6 us for the
+            // stencil at any occupancy — crossing at ~5.3 % of the halo box (profiles/r2_notes.md); wider slices move more
+            // taps per listed voxel in the same instructions, so their crossing is higher
             static const double forced = SN_ENV("SN_FWD_TILE_PCT") ? atof(SN_ENV("SN_FWD_TILE_PCT")) : -1.0;
-            const double pct = forced >= 0.0 ? forced : 10.0;
+            const double pct = forced >= 0.0 ? forced : (kx * ky <= 32 ? 5.5 : 7.0);
             p.dense_thresh = (int)((double)p.HZ * p.HX * (p.IY + ky - 1) * pct / 100.0);
         }
     }
