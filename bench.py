@@ -664,6 +664,9 @@ def main():
     # the same step fed with byte occupancy grids (what ToFullDense produces; module extension): 8x fewer PCIe bytes
     xh8 = [h.to(torch.uint8).pin_memory() for h in xh]
     e2e_u8_value, h2d_u8 = e2e_measure(xh8, [pool[0][1].float(), pool[1][1].float()])
+    # ... and with one BIT per voxel (ops.pack_occupancy, SN_BITS): 64x fewer bytes than the reference's float64 grids
+    xhb = [ops.pack_occupancy(h).pin_memory() for h in xh]
+    e2e_bits_value, h2d_bits = e2e_measure(xhb, [pool[0][1].float(), pool[1][1].float()])
 
     # ------------------------------------------------ config 2 (ii): full training_step semantics — the module step with the
     # drop-in GENEO_Tversky_Loss (fused criterion kernels) instead of a fixed upstream gradient
@@ -896,6 +899,9 @@ def main():
                        "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * bytes_per_set / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "uint8_occupancy_input": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8},
+                    "packed_occupancy_input": {"value": e2e_bits_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bits,
+                                               "note": "one bit per voxel (ops.pack_occupancy / TS40KDeviceLoader(dtype=torch.int32)); "
+                                                       "same predictions and gradients as the float32 path, bit for bit"},
                     "h2d_GBps_measured": h2d_gbps, "pcie_bound": B_PER_GPU * world / (h2d / (h2d_gbps * 1e9)),
                     "pcie_note": "pcie_bound = grids/s at which the H2D copy of x alone saturates the measured host->device rate "
                                  "(all ranks copying at once)",

@@ -44,6 +44,8 @@ extern "C" {
 #define SN_U8 2  /* occupancy bytes (uint8 / bool); accepted by sn_grid_prepare and as a target dtype */
 #define SN_I32 3 /* integer targets (sn_confusion_counts only) */
 #define SN_I64 4
+#define SN_BITS 5 /* occupancy, one BIT per voxel: bit i % 32 of 32-bit word i / 32 <-> flat voxel index i (sn_grid_prepare only;
+                   * 64x fewer bytes than the float64 grids of the reference's ToFullDense, torch_transforms.py:33-40) */
 
 /* ---- GENEO operator kinds (core/models/geneos/) -------------------------------------- */
 #define SN_KIND_CYLINDER_V1 0 /* cylinder.py:30-140   cylinder_kernel   params: radius, sigma                */
@@ -255,6 +257,7 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
  *   then from byte 8 * SN_STATE_WORDS one occupancy BIT per voxel (bit i % 32 of 32-bit word i / 32 <-> flat voxel
  *   index i) + 4 padding words: the occupancy-driven forward lists the non-zero voxels of a halo box from these words
  *   instead of scanning floats — then the tile list ([3] entries, 32-bit tile ids; ABI v4).
+ * x may also be SN_BITS (packed occupancy, ceil(n / 32) words): x32 receives 0 / 1 and the words become the state's mask.
  * nnz: DEVICE buffer of sn_grid_state_bytes(n) bytes, 16-byte aligned; counters zeroed and bits written by the call.
  * x and x32 16-byte aligned. */
 #define SN_STATE_WORDS 8

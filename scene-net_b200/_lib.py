@@ -12,7 +12,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCENENET_B200_LIB", os.path.join(PKG, "libscenenet_b200.so"))  # override: experiments only
 
-SN_F32, SN_F64, SN_U8, SN_I32, SN_I64 = 0, 1, 2, 3, 4
+SN_F32, SN_F64, SN_U8, SN_I32, SN_I64, SN_BITS = 0, 1, 2, 3, 4, 5
 SN_PATH_AUTO, SN_PATH_DENSE, SN_PATH_SPARSE = 0, 1, 2
 SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE = 0, 1, 2
 SN_MAX_GENEOS = 16

@@ -121,7 +121,8 @@ class TS40KDeviceLoader:
 
     sources: a `TS40K` dataset, or a sequence of `.npy` paths / [N,4] float64 arrays.
     Yields x = occupancy and y = occupancy of `keep_labels` points, both [B,1,n_z,n_x,n_y] in `dtype`
-    (float64 = what the reference's ToTensor hands the model; uint8 = 8x fewer bytes, the model accepts both).
+    (float64 = what the reference's ToTensor hands the model; uint8 = 8x fewer bytes; int32 = x packed to one bit per
+    voxel [B,1,n_z,n_x,n_y/32], 64x fewer bytes, y uint8 — the model accepts all of them).
     Empty / unreadable samples are replaced by another random sample like in the reference's `__getitem__`.
     """
 
@@ -133,8 +134,8 @@ class TS40KDeviceLoader:
         self.sources: List[Source] = list(sources)
         if batch_size < 1:
             raise ValueError("batch_size must be positive")
-        if dtype not in (torch.float64, torch.float32, torch.uint8):
-            raise TypeError("dtype must be float64, float32 or uint8")
+        if dtype not in (torch.float64, torch.float32, torch.uint8, torch.int32):
+            raise TypeError("dtype must be float64, float32, uint8 or int32 (packed occupancy bits, ops.pack_occupancy)")
         self.batch_size, self.keep_labels, self.vxg_size = int(batch_size), tuple(float(k) for k in keep_labels), tuple(int(v) for v in vxg_size)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
@@ -224,6 +225,9 @@ class TS40KDeviceLoader:
         x, y = out["occ"].unsqueeze(1), out["occ_keep"].unsqueeze(1)
         if self.dtype == torch.uint8:
             x, y = x.to(torch.uint8), y.to(torch.uint8)
+        elif self.dtype == torch.int32:  # one bit per voxel for the model input, bytes for the target
+            from ... import ops
+            x, y = ops.pack_occupancy(x), y.to(torch.uint8)
         return x, y
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:

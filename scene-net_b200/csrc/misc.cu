@@ -189,6 +189,40 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float* __restrict_
     add_count(cnt, dns, nun, nnz);
 }
 
+// packed occupancy (one bit per voxel) -> float32 0 / 1 + the state buffer: a warp takes 32 words; every store instruction
+// of the warp writes 512 contiguous bytes (lane l: 4 voxels of word 4 j + l / 8)
+__global__ void __launch_bounds__(256) prepare_bits_kernel(const unsigned* __restrict__ in, float* __restrict__ out, long long n,
+                                                           unsigned long long* nnz, unsigned* __restrict__ mask) {
+    const long long nw = (n + 31) >> 5;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    unsigned cnt = 0, dns = 0;
+    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nw; wb += stride) {
+        unsigned w = wb + lane < nw ? __ldg(in + wb + lane) : 0u;
+        if (wb + lane == nw - 1 && (n & 31)) w &= (1u << (n & 31)) - 1u;  // bits past the last voxel are not part of the grid
+        if (wb + lane < nw) {
+            mask[wb + lane] = w;
+            cnt += __popc(w);
+            dns += __popc(w) >= kDenseWordBits ? 1u : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned v = __shfl_sync(0xffffffffu, w, 4 * j + (lane >> 3));
+            const unsigned b = (v >> ((lane & 7) * 4)) & 0xfu;
+            const long long vox = (wb + 4 * j + (lane >> 3)) * 32 + (lane & 7) * 4;
+            const float4 o = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)(b >> 3));
+            if (vox + 3 < n) {
+                *reinterpret_cast<float4*>(out + vox) = o;
+            } else {
+                if (vox < n) out[vox] = o.x;
+                if (vox + 1 < n) out[vox + 1] = o.y;
+                if (vox + 2 < n) out[vox + 2] = o.z;
+            }
+        }
+    }
+    add_count(cnt, dns, 0u, nnz);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) threshold_kernel(const T* __restrict__ p, T tau, long long n, T* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -252,7 +286,7 @@ extern "C" int64_t sn_grid_state_bytes(int64_t n) {
 
 extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, unsigned long long* nnz, void* stream) {
     if (!x || !nnz || n < 0) return SN_ERR_BAD_ARG;
-    if (dtype != SN_F32 && dtype != SN_F64 && dtype != SN_U8) return SN_ERR_BAD_ARG;
+    if (dtype != SN_F32 && dtype != SN_F64 && dtype != SN_U8 && dtype != SN_BITS) return SN_ERR_BAD_ARG;
     if (dtype != SN_F32 && !x32) return SN_ERR_BAD_ARG;
     if (dtype == SN_F32 && x32 && (const void*)x32 != x) return SN_ERR_BAD_ARG;  // float32 grids are used in place
     if (((uintptr_t)x & 15) || ((uintptr_t)x32 & 15) || ((uintptr_t)nnz & 15)) return SN_ERR_ALIGN;
@@ -265,6 +299,8 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
         sn::prepare_f64_kernel<<<sn::grid_for(n / 8 + 1, 256), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
     else if (dtype == SN_U8)
         sn::prepare_u8_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz, mask);
+    else if (dtype == SN_BITS)
+        sn::prepare_bits_kernel<<<sn::grid_for(n / 32 + 1, 256), 256, 0, s>>>((const unsigned*)x, x32, n, nnz, mask);
     else
         sn::count_f32_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const float*)x, n, nnz, mask);
     SN_LAUNCH_CHECK();

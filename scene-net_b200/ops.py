@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import SN_F32, SN_F64, SN_I32, SN_I64, SN_U8, ModelDesc, check, lib
+from ._lib import SN_BITS, SN_F32, SN_F64, SN_I32, SN_I64, SN_U8, ModelDesc, check, lib
 
 _DT = {torch.float32: SN_F32, torch.float64: SN_F64}
 
@@ -238,6 +238,23 @@ def _state_words(n: int) -> int:
     return int(lib.sn_grid_state_bytes(n)) // 8
 
 
+def pack_occupancy(x: torch.Tensor) -> torch.Tensor:
+    """[..., Y] grid (any dtype; non-zero = occupied; Y a multiple of 32) -> int32 [..., Y / 32] with one bit per voxel
+    (bit i % 32 of word i / 32 <-> flat voxel index i): the most compact form the modules accept as input — 64x fewer
+    bytes than the float64 occupancy grids of the reference's ToFullDense.  Plain torch ops (not a hot path)."""
+    if x.shape[-1] % 32:
+        raise ValueError(f"the last dimension must be a multiple of 32 to pack rows into whole words, got {x.shape[-1]}")
+    b = (x.reshape(*x.shape[:-1], x.shape[-1] // 32, 32) != 0).to(torch.int64)
+    w = (b << torch.arange(32, device=x.device, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
+def unpack_occupancy(bits: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """inverse of pack_occupancy (tests, debugging)"""
+    w = bits.to(torch.int64) & 0xffffffff
+    return ((w.unsqueeze(-1) >> torch.arange(32, device=bits.device, dtype=torch.int64)) & 1).reshape(*bits.shape[:-1], -1).to(dtype)
+
+
 def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
     (x itself for float32 input), nnz the grid state buffer as an int64 device tensor ([0] = number of non-zero
@@ -249,21 +266,24 @@ def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     _need_cuda(x, "x")
     if x.dtype == torch.bool:
         x = x.view(torch.uint8)
-    if x.dtype not in (torch.float64, torch.float32, torch.uint8):
-        raise TypeError(f"voxel grids must be float64, float32, uint8 or bool, got {x.dtype}")
+    if x.dtype not in (torch.float64, torch.float32, torch.uint8, torch.int32):
+        raise TypeError(f"voxel grids must be float64, float32, uint8, bool or int32 (packed occupancy bits), got {x.dtype}")
     x = x.contiguous()
     if x.data_ptr() % 16:
         x = x.clone()
-    x32 = x if x.dtype == torch.float32 else torch.empty(x.shape, dtype=torch.float32, device=x.device)
-    if x.numel() == 0:
-        return x32, torch.zeros(2, dtype=torch.int64, device=x.device)
-    nnz = torch.empty(_state_words(x.numel()), dtype=torch.int64, device=x.device)
-    dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8}[x.dtype]
+    packed = x.dtype == torch.int32  # pack_occupancy: [..., Y / 32] words, one bit per voxel
+    shape = (*x.shape[:-1], x.shape[-1] * 32) if packed else x.shape
+    n = x.numel() * (32 if packed else 1)
+    x32 = x if x.dtype == torch.float32 else torch.empty(shape, dtype=torch.float32, device=x.device)
+    if n == 0:
+        return x32, torch.zeros(8, dtype=torch.int64, device=x.device)
+    nnz = torch.empty(_state_words(n), dtype=torch.int64, device=x.device)
+    dt = {torch.float64: SN_F64, torch.float32: SN_F32, torch.uint8: SN_U8, torch.int32: SN_BITS}[x.dtype]
     with _on_device(x.device):
         if stream is not None:
             stream.wait_stream(current_stream_obj(x.device))  # x (and any copy made above) is ready
         st = _stream() if stream is None else stream.cuda_stream
-        check(lib.sn_grid_prepare(x.data_ptr(), dt, x.numel(), None if x.dtype == torch.float32 else x32.data_ptr(),
+        check(lib.sn_grid_prepare(x.data_ptr(), dt, n, None if x.dtype == torch.float32 else x32.data_ptr(),
                                   nnz.data_ptr(), st), "sn_grid_prepare")
     return x32, nnz
 
@@ -354,9 +374,9 @@ def select_paths(x: torch.Tensor, kernel_size) -> tuple:
     """(forward mode, backward mode) the device-side selection would pick for grids like `x` — reads the grid state
     (non-zero count, clustering statistic) on the host (one synchronisation; meant for capture time, see
     graphs.GraphedStep)."""
-    B, Z, X, Y = _grid_dims(x)
     kz, kx, ky = (int(v) for v in kernel_size)
-    _, st = prepare(x.detach())
+    x32, st = prepare(x.detach())
+    B, Z, X, Y = _grid_dims(x32)
     n, dw = (int(v) for v in st[:3:2].tolist())
     return (int(lib.sn_select_fwd_path_state(n, dw, B, Z, X, Y, kz, kx, ky)), int(lib.sn_select_path(1, n, B, Z, X, Y, kz, kx, ky)))
 
