@@ -361,7 +361,7 @@ def test_empty_batch_and_errors():
     with pytest.raises(ValueError):
         m(torch.zeros(1, 2, 8, 8, 8, dtype=torch.float64, device=DEV))
     with pytest.raises(TypeError):
-        m(torch.zeros(1, 1, 8, 8, 8, dtype=torch.int32, device=DEV))
+        m(torch.zeros(1, 1, 8, 8, 8, dtype=torch.int64, device=DEV))  # (int32 = packed occupancy bits since ABI v4)
 
 
 def test_byte_occupancy_input_equals_float_input():
