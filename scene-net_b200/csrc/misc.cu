@@ -84,82 +84,97 @@ __device__ __forceinline__ unsigned store_mask_words(unsigned bits, long long wb
     return 0u;
 }
 
+// bits a (even positions) and b (odd positions) of two 16-bit halves interleaved into one 32-bit word
+__device__ __forceinline__ unsigned interleave16(unsigned a, unsigned b) {
+    a = (a | (a << 8)) & 0x00ff00ffu; b = (b | (b << 8)) & 0x00ff00ffu;
+    a = (a | (a << 4)) & 0x0f0f0f0fu; b = (b | (b << 4)) & 0x0f0f0f0fu;
+    a = (a | (a << 2)) & 0x33333333u; b = (b | (b << 2)) & 0x33333333u;
+    a = (a | (a << 1)) & 0x55555555u; b = (b | (b << 1)) & 0x55555555u;
+    return a | (b << 1);
+}
+
+// float64 grids (what the reference's ToTensor hands over).  A warp takes 256 consecutive voxels per step as four
+// instructions of 32 x 16 bytes: every load instruction reads 512 contiguous bytes and every store instruction writes 256
+// (round 1's version gave each lane 8 consecutive voxels: 16-byte accesses at a 64- / 32-byte lane stride, half sectors per
+// instruction — ncu 16.4 us for 101 MB).  The occupancy bits of a 64-voxel group come from two ballots (even / odd voxels of
+// the lanes' pairs) interleaved by lanes 0 / 1 into the two mask words.
 __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
                                                           unsigned long long* nnz, unsigned* __restrict__ mask) {
-    // A lane owns 8 consecutive voxels per step: four 16-byte loads in flight (one per step left the pass at 0.73 of the
-    // HBM copy rate), two 16-byte stores, and 4 lanes per mask word (two shuffle steps).  Warp-uniform trip count (the
-    // mask words are assembled across lanes): a lane past the end contributes zeros.
-    const long long nc = (n + 7) >> 3;  // 8-voxel chunks; the last one may be partial
+    const long long ngroups = (n + 255) >> 8;  // 256-voxel groups; the last one may be partial
     const long long nw = (n + 31) >> 5;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
     unsigned cnt = 0, dns = 0, nun = 0;
-    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
-        const long long i = wb + lane;
-        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (8 * i + 7 < n) {
-            double2 v[4];
+    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += wstride) {
+        const long long vb = g << 8;
+        double2 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const double2*>(in)[4 * i + u];
+        for (int j = 0; j < 4; ++j) {
+            const long long p = vb + 64 * j + 2 * lane;
+            v[j] = make_double2(0.0, 0.0);
+            if (p + 1 < n)
+                v[j] = reinterpret_cast<const double2*>(in)[p >> 1];
+            else if (p < n)
+                v[j].x = in[p];
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                o[2 * u] = (float)v[u].x;
-                o[2 * u + 1] = (float)v[u].y;
-            }
-            float4* dst = reinterpret_cast<float4*>(out) + 2 * i;
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-            for (int q = 0; q < 8; ++q)
-                if (8 * i + q < n) {
-                    o[q] = (float)in[8 * i + q];
-                    out[8 * i + q] = o[q];
+        for (int j = 0; j < 4; ++j) {
+            const long long p = vb + 64 * j + 2 * lane;
+            const float ox = (float)v[j].x, oy = (float)v[j].y;
+            if (p + 1 < n)
+                reinterpret_cast<float2*>(out)[p >> 1] = make_float2(ox, oy);
+            else if (p < n)
+                out[p] = ox;
+            const unsigned b0 = __ballot_sync(0xffffffffu, ox != 0.f), b1 = __ballot_sync(0xffffffffu, oy != 0.f);
+            const unsigned u0 = __ballot_sync(0xffffffffu, ox == 1.f), u1 = __ballot_sync(0xffffffffu, oy == 1.f);
+            if (lane < 2) {  // lane h assembles mask word (vb + 64 j) / 32 + h from the 16-bit halves of the ballots
+                const unsigned w = interleave16((b0 >> (16 * lane)) & 0xffffu, (b1 >> (16 * lane)) & 0xffffu);
+                const unsigned o1 = interleave16((u0 >> (16 * lane)) & 0xffffu, (u1 >> (16 * lane)) & 0xffffu);
+                const long long wi = ((vb + 64 * j) >> 5) + lane;
+                if (wi < nw) {
+                    mask[wi] = w;
+                    cnt += __popc(w);
+                    nun += __popc(w & ~o1);
+                    dns += __popc(w) >= kDenseWordBits ? 1u : 0u;
                 }
+            }
         }
-        unsigned bits = 0, ones = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            bits |= (o[q] != 0.f ? 1u : 0u) << q;
-            ones |= (o[q] == 1.f ? 1u : 0u) << q;
-        }
-        cnt += __popc(bits);
-        nun += __popc(bits & ~ones);
-        dns += store_mask_words<8>(bits, wb, mask, nw);
     }
     add_count(cnt, dns, nun, nnz);
 }
 
+// occupancy bytes (uint8 / bool): a lane takes 4 voxels per instruction, so that a load instruction reads 128 contiguous
+// bytes and a store instruction writes 512 (round 1: one 16-byte load and four 16-byte stores per lane at a 64-byte lane
+// stride — 16.5 us under ncu for 8 MB in, 34 MB out; the float64 kernel was no slower)
 __global__ void __launch_bounds__(256) prepare_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n,
                                                          unsigned long long* nnz, unsigned* __restrict__ mask) {
-    const long long nc = (n + 15) >> 4;  // 16-voxel chunks; the last one may be partial
+    const long long nq = (n + 3) >> 2;  // 4-voxel chunks; the last one may be partial
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     unsigned cnt = 0, dns = 0, nun = 0;
-    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
+    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nq; wb += stride) {
         const long long i = wb + lane;
-        unsigned bits = 0, big = 0;
-        if (16 * i + 15 < n) {
-            const uint4 v = reinterpret_cast<const uint4*>(in)[i];
-            const unsigned w[4] = {v.x, v.y, v.z, v.w};
-            float4* o = reinterpret_cast<float4*>(out) + 4 * i;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned b0 = w[k] & 0xffu, b1 = (w[k] >> 8) & 0xffu, b2 = (w[k] >> 16) & 0xffu, b3 = w[k] >> 24;
-                o[k] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
-                bits |= ((b0 != 0 ? 1u : 0u) | (b1 != 0 ? 2u : 0u) | (b2 != 0 ? 4u : 0u) | (b3 != 0 ? 8u : 0u)) << (4 * k);
-                big |= ((b0 > 1 ? 1u : 0u) | (b1 > 1 ? 2u : 0u) | (b2 > 1 ? 4u : 0u) | (b3 > 1 ? 8u : 0u)) << (4 * k);
-            }
+        unsigned w = 0;
+        if (4 * i + 3 < n) {
+            w = reinterpret_cast<const unsigned*>(in)[i];
         } else {
-            for (long long j = 16 * i; j < n; ++j) {
-                const unsigned char b = in[j];
-                out[j] = (float)b;
-                bits |= (b != 0 ? 1u : 0u) << (int)(j - 16 * i);
-                big |= (b > 1 ? 1u : 0u) << (int)(j - 16 * i);
-            }
+            for (int q = 0; q < 4; ++q)
+                if (4 * i + q < n) w |= (unsigned)in[4 * i + q] << (8 * q);
         }
+        const unsigned b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
+        const float4 o = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+        if (4 * i + 3 < n) {
+            reinterpret_cast<float4*>(out)[i] = o;
+        } else {
+            if (4 * i < n) out[4 * i] = o.x;
+            if (4 * i + 1 < n) out[4 * i + 1] = o.y;
+            if (4 * i + 2 < n) out[4 * i + 2] = o.z;
+        }
+        const unsigned bits = (b0 != 0 ? 1u : 0u) | (b1 != 0 ? 2u : 0u) | (b2 != 0 ? 4u : 0u) | (b3 != 0 ? 8u : 0u);
+        const unsigned big = (b0 > 1 ? 1u : 0u) | (b1 > 1 ? 2u : 0u) | (b2 > 1 ? 4u : 0u) | (b3 > 1 ? 8u : 0u);
         cnt += __popc(bits);
         nun += __popc(big);
-        dns += store_mask_words<16>(bits, wb, mask, (n + 31) >> 5);
+        dns += store_mask_words<4>(bits, wb, mask, (n + 31) >> 5);
     }
     add_count(cnt, dns, nun, nnz);
 }
@@ -296,9 +311,16 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     if (n == 0) return SN_OK;
     unsigned* mask = reinterpret_cast<unsigned*>(nnz + SN_STATE_WORDS);  // occupancy bits follow the counters
     if (dtype == SN_F64)
-        sn::prepare_f64_kernel<<<sn::grid_for(n / 8 + 1, 256), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
+    {
+        // balanced: every warp takes the same number of 256-voxel groups (3.46 groups per warp left a quarter of the warps one
+        // group short of the others' four)
+        const long long ngroups = (n + 255) >> 8, cap = (long long)sn::kNumSMs * 8;
+        const long long iters = sn::ceil_div64(ngroups, cap * 8);
+        const long long blocks = sn::ceil_div64(ngroups, iters * 8);
+        sn::prepare_f64_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
+    }
     else if (dtype == SN_U8)
-        sn::prepare_u8_kernel<<<sn::grid_for(n / 16 + 1, 256 * 2), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz, mask);
+        sn::prepare_u8_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz, mask);
     else if (dtype == SN_BITS)
         sn::prepare_bits_kernel<<<sn::grid_for(n / 32 + 1, 256), 256, 0, s>>>((const unsigned*)x, x32, n, nnz, mask);
     else

@@ -34,6 +34,7 @@ REPS = {"r1b": [("gpurun_out/prof_r1_step.ncu-rep", "r1b_ncu_step_kernels.csv"),
         # third part of the round: mask-driven occupancy forward (1.6 % and empty grids), scanning kernel before it, prepare with the bit mask
         "r1c": [("gpurun_out/prof_fo_r1h.ncu-rep", "r1c_ncu_fwd_occ.csv"), ("gpurun_out/prof_fo0_r1d.ncu-rep", "r1c_ncu_fwd_occ_empty_grids.csv"),
                 ("gpurun_out/prof_fs_r1c.ncu-rep", "r1c_ncu_fwd_scan_before.csv"), ("gpurun_out/prof_prep_r1h.ncu-rep", "r1c_ncu_prepare.csv")]}
+REPS["r2"] = [("gpurun_out/prof_fwd_r2j.ncu-rep", "r2_ncu_fwd_before_polish.csv"), ("gpurun_out/prof_fwd_r2n.ncu-rep", "r2_ncu_fwd_occ.csv")]
 for rep, name in REPS.get(tag, []):
     if not os.path.exists(rep):
         continue
@@ -46,4 +47,28 @@ for rep, name in REPS.get(tag, []):
         w.writerow(["metric", "unit"] + [r[cols[0]][:60] for r in rr[2:]])
         for c in cols[1:]:
             w.writerow([h[c], units[c]] + [r[c] for r in rr[2:]])
+if tag == "r2":
+    # DRAM bytes per launch for bench.py's roofline.traffic: the forward from this round's capture, the kernels that did not
+    # change from round 1's (profiles/r1b_traffic.json)
+    import json
+    old = json.load(open(f"{out}/r1b_traffic.json"))
+    rep = "gpurun_out/prof_fwd_r2n.ncu-rep"
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, units = rr[0], rr[1]
+    def val(row, m):
+        i = h.index(m)
+        v = float(row[i].replace(",", ""))
+        return int(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]])
+    row = rr[-1]
+    new = {"source": "ncu --set full --clock-control none, one launch each, config 2 (B=32, 64^3, (9,5,5), float64 boundary); fwd_occ_kernel: "
+                     "gpurun_out/prof_fwd_r2n.ncu-rep (scratch/prof_fwd.py, round 2) -> profiles/r2_ncu_fwd_occ.csv; the other kernels are unchanged "
+                     "since round 1 (profiles/r1b_traffic.json); dram__bytes_read.sum + dram__bytes_write.sum",
+           "fwd_occ_kernel": {"dram_bytes_read": val(row, "dram__bytes_read.sum"), "dram_bytes_write": val(row, "dram__bytes_write.sum"),
+                              "algorithmic_bytes": 100663296,
+                              "note": "x arrives as one occupancy bit per voxel from the state buffer (1 MB); pred (67 MB float64) is written "
+                                      "through the 126 MB L2 and mostly still dirty there when the kernel ends"}}
+    for k in ("stencil_fwd_kernel", "tapgrad_sparse_kernel", "g0_kernel", "prepare_f64_kernel"):
+        new[k] = old[k]
+    json.dump(new, open(f"{out}/r2_traffic.json", "w"), indent=1)
 print("ok", os.listdir(out))
