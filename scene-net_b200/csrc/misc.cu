@@ -84,61 +84,52 @@ __device__ __forceinline__ unsigned store_mask_words(unsigned bits, long long wb
     return 0u;
 }
 
-// bits a (even positions) and b (odd positions) of two 16-bit halves interleaved into one 32-bit word
-__device__ __forceinline__ unsigned interleave16(unsigned a, unsigned b) {
-    a = (a | (a << 8)) & 0x00ff00ffu; b = (b | (b << 8)) & 0x00ff00ffu;
-    a = (a | (a << 4)) & 0x0f0f0f0fu; b = (b | (b << 4)) & 0x0f0f0f0fu;
-    a = (a | (a << 2)) & 0x33333333u; b = (b | (b << 2)) & 0x33333333u;
-    a = (a | (a << 1)) & 0x55555555u; b = (b | (b << 1)) & 0x55555555u;
-    return a | (b << 1);
-}
-
-// float64 grids (what the reference's ToTensor hands over).  A warp takes 256 consecutive voxels per step as four
-// instructions of 32 x 16 bytes: every load instruction reads 512 contiguous bytes and every store instruction writes 256
-// (round 1's version gave each lane 8 consecutive voxels: 16-byte accesses at a 64- / 32-byte lane stride, half sectors per
-// instruction — ncu 16.4 us for 101 MB).  The occupancy bits of a 64-voxel group come from two ballots (even / odd voxels of
-// the lanes' pairs) interleaved by lanes 0 / 1 into the two mask words.
+// float64 grids (what the reference's ToTensor hands over).  Measured alternatives (CUDA-graph replay, config 2, 101 MB): this
+// version — a lane owns 8 consecutive voxels, four 16-byte loads and two 16-byte stores — 20.7 us; fully coalesced 8-byte
+// loads / 4-byte stores with the ballot as mask word 22.8 us (2.7 x the memory instructions); coalesced 16-byte loads with two
+// interleaved ballots per word 34.8 us (instruction-bound).  ~5 us of each figure are the memset node of the counters and the
+// node-to-node latency inside the graph (a float32 grid that is only counted, 34 MB, takes 16.5 us).
 __global__ void __launch_bounds__(256, 4) prepare_f64_kernel(const double* __restrict__ in, float* __restrict__ out, long long n,
                                                           unsigned long long* nnz, unsigned* __restrict__ mask) {
-    const long long ngroups = (n + 255) >> 8;  // 256-voxel groups; the last one may be partial
+    // A lane owns 8 consecutive voxels per step: four 16-byte loads in flight (one per step left the pass at 0.73 of the
+    // HBM copy rate), two 16-byte stores, and 4 lanes per mask word (two shuffle steps).  Warp-uniform trip count (the
+    // mask words are assembled across lanes): a lane past the end contributes zeros.
+    const long long nc = (n + 7) >> 3;  // 8-voxel chunks; the last one may be partial
     const long long nw = (n + 31) >> 5;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
     unsigned cnt = 0, dns = 0, nun = 0;
-    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += wstride) {
-        const long long vb = g << 8;
-        double2 v[4];
+    for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < nc; wb += stride) {
+        const long long i = wb + lane;
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (8 * i + 7 < n) {
+            double2 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long p = vb + 64 * j + 2 * lane;
-            v[j] = make_double2(0.0, 0.0);
-            if (p + 1 < n)
-                v[j] = reinterpret_cast<const double2*>(in)[p >> 1];
-            else if (p < n)
-                v[j].x = in[p];
-        }
+            for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const double2*>(in)[4 * i + u];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long p = vb + 64 * j + 2 * lane;
-            const float ox = (float)v[j].x, oy = (float)v[j].y;
-            if (p + 1 < n)
-                reinterpret_cast<float2*>(out)[p >> 1] = make_float2(ox, oy);
-            else if (p < n)
-                out[p] = ox;
-            const unsigned b0 = __ballot_sync(0xffffffffu, ox != 0.f), b1 = __ballot_sync(0xffffffffu, oy != 0.f);
-            const unsigned u0 = __ballot_sync(0xffffffffu, ox == 1.f), u1 = __ballot_sync(0xffffffffu, oy == 1.f);
-            if (lane < 2) {  // lane h assembles mask word (vb + 64 j) / 32 + h from the 16-bit halves of the ballots
-                const unsigned w = interleave16((b0 >> (16 * lane)) & 0xffffu, (b1 >> (16 * lane)) & 0xffffu);
-                const unsigned o1 = interleave16((u0 >> (16 * lane)) & 0xffffu, (u1 >> (16 * lane)) & 0xffffu);
-                const long long wi = ((vb + 64 * j) >> 5) + lane;
-                if (wi < nw) {
-                    mask[wi] = w;
-                    cnt += __popc(w);
-                    nun += __popc(w & ~o1);
-                    dns += __popc(w) >= kDenseWordBits ? 1u : 0u;
-                }
+            for (int u = 0; u < 4; ++u) {
+                o[2 * u] = (float)v[u].x;
+                o[2 * u + 1] = (float)v[u].y;
             }
+            float4* dst = reinterpret_cast<float4*>(out) + 2 * i;
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            for (int q = 0; q < 8; ++q)
+                if (8 * i + q < n) {
+                    o[q] = (float)in[8 * i + q];
+                    out[8 * i + q] = o[q];
+                }
         }
+        unsigned bits = 0, ones = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            bits |= (o[q] != 0.f ? 1u : 0u) << q;
+            ones |= (o[q] == 1.f ? 1u : 0u) << q;
+        }
+        cnt += __popc(bits);
+        nun += __popc(bits & ~ones);
+        dns += store_mask_words<8>(bits, wb, mask, nw);
     }
     add_count(cnt, dns, nun, nnz);
 }
@@ -311,14 +302,7 @@ extern "C" int sn_grid_prepare(const void* x, int dtype, int64_t n, float* x32, 
     if (n == 0) return SN_OK;
     unsigned* mask = reinterpret_cast<unsigned*>(nnz + SN_STATE_WORDS);  // occupancy bits follow the counters
     if (dtype == SN_F64)
-    {
-        // balanced: every warp takes the same number of 256-voxel groups (3.46 groups per warp left a quarter of the warps one
-        // group short of the others' four)
-        const long long ngroups = (n + 255) >> 8, cap = (long long)sn::kNumSMs * 8;
-        const long long iters = sn::ceil_div64(ngroups, cap * 8);
-        const long long blocks = sn::ceil_div64(ngroups, iters * 8);
-        sn::prepare_f64_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
-    }
+        sn::prepare_f64_kernel<<<sn::grid_for(n / 8 + 1, 256), 256, 0, s>>>((const double*)x, x32, n, nnz, mask);
     else if (dtype == SN_U8)
         sn::prepare_u8_kernel<<<sn::grid_for(n / 4 + 1, 256 * 4), 256, 0, s>>>((const unsigned char*)x, x32, n, nnz, mask);
     else if (dtype == SN_BITS)
