@@ -465,6 +465,7 @@ def main():
                          "config5 = KITTI-shaped scans: voxelize + GENEO inference")
     ap.add_argument("--kernel", type=int, default=9, help="config4: cubic kernel extent (9, 11, 13, 15)")
     ap.add_argument("--no-sub-records", action="store_true", help="N > 1: do not add the short config 4 / config 5 records")
+    ap.add_argument("--brief", action="store_true", help="skip the rank-0-only kernel roofline / voxelization / CPU sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -754,7 +755,7 @@ def main():
     roof = None
     cpu_base = None
     vox = None
-    if rank == 0:
+    if rank == 0 and not args.brief:
         T = KERNEL[0] * KERNEL[1] * KERNEL[2]
         V = B_PER_GPU * GRID[0] * GRID[1] * GRID[2]
         peak_tf = ops.fp32_peak_probe(2000, device)

@@ -103,3 +103,49 @@ def test_sparse_tapgrad_full_size_properties():
     assert torch.allclose(Wab, 2.0 * Wa + Wb, rtol=0, atol=2e-5 * scale)
     Wd = ops.tapgrad(x, g0, ks, mode=SN_TAPGRAD_DENSE)
     assert torch.allclose(Wa, Wd, rtol=0, atol=2e-5 * float(Wd.abs().max()))
+
+
+FUSED_CASES = [
+    # B, grid (Z,X,Y), kernel, density, binary, dtype
+    (2, (64, 64, 64), (9, 5, 5), 0.016, True, torch.float64),     # config-2 shape
+    (2, (64, 64, 64), (9, 5, 5), 0.016, False, torch.float32),    # density values, float32 predictions
+    (3, (20, 17, 32), (9, 5, 5), 0.05, False, torch.float64),     # ragged z / x, 8 x 16 x 32 tiles
+    (1, (32, 32, 32), (11, 11, 11), 0.016, True, torch.float64),  # 6 tap chunks
+    (1, (24, 24, 64), (15, 15, 15), 0.016, True, torch.float64),  # 14 tap chunks, ring of 32 z-rows
+    (2, (8, 8, 128), (9, 5, 5), 0.016, True, torch.float64),      # several y tiles, one z tile
+    (1, (40, 8, 32), (1, 1, 1), 0.5, False, torch.float64),       # single tap
+    (2, (16, 16, 32), (4, 6, 5), 0.02, False, torch.float64),     # even extents (asymmetric 'same' padding)
+    (1, (72, 24, 64), (9, 5, 5), 0.3, False, torch.float64),      # lists longer than one window
+    (2, (64, 64, 64), (9, 5, 5), 0.0, True, torch.float64),       # empty grids
+]
+
+
+@pytest.mark.parametrize("B,grid,ks,density,binary,dt", FUSED_CASES)
+def test_bwd_entry_point_equals_g0_plus_tapgrad(B, grid, ks, density, binary, dt):
+    """sn_scenenet_bwd (G0 pass + tap gradient in one call, with and without the grid state buffer) agrees with the float64
+    cross-correlation of the same G0 and is bit-identical to sn_scenenet_g0 + sn_scenenet_tapgrad in every mode."""
+    from scenenet_b200 import ops
+    from scenenet_b200._lib import SN_TAPGRAD_AUTO, SN_TAPGRAD_DENSE, SN_TAPGRAD_SPARSE
+    x, _ = _inputs(B, grid, density, seed=hash((B, grid, ks)) % 1000, binary=binary)
+    g = torch.Generator().manual_seed(11)
+    pred = torch.relu(torch.tanh(torch.randn((B, 1, *grid), generator=g, dtype=torch.float64))).to(dt).to(DEV)
+    dpred = torch.randn((B, 1, *grid), generator=g, dtype=torch.float64).to(dt).to(DEV)
+    x32, state = ops.prepare(x)
+    g0 = ops.g0(pred, dpred)
+    ref = _ref_tapgrad(x, g0, ks)
+    tol = 2e-6 * _ref_tapgrad(x.abs(), g0.abs(), ks) + 1e-12
+    Wf = ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_SPARSE)
+    assert bool(((Wf - ref).abs() <= tol).all()), f"max err {(Wf - ref).abs().max():.3e}"
+    # deterministic, and the state buffer serves a second backward (the last CTA resets the ticket)
+    assert torch.equal(Wf, ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_SPARSE))
+    # device-side choice: the occupancy-driven kernel below the occupancy threshold, the dense stencil above it
+    Wa = ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_AUTO)
+    if density <= 0.05:
+        assert torch.equal(Wa, Wf)
+    elif ks[2] in (3, 5, 6, 7, 9, 11, 13, 15):
+        assert torch.equal(Wa, ops.scenenet_bwd(x32, pred, dpred, ks, mode=SN_TAPGRAD_DENSE))
+    else:  # widths without a dense instantiation always take the occupancy-driven kernel
+        assert torch.equal(Wa, Wf)
+    # without a state buffer: the two-kernel path
+    assert torch.equal(ops.scenenet_bwd(x32, pred, dpred, ks, mode=SN_TAPGRAD_SPARSE), ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_SPARSE))
+    assert torch.equal(ops.tapgrad(x32, g0, ks, nnz=state, mode=SN_TAPGRAD_SPARSE), Wf)
