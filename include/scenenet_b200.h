@@ -270,6 +270,12 @@ int sn_cast_u8_to_f32(const unsigned char* in, float* out, int64_t n, void* stre
 /* prob_to_label (utils/voxelization.py:304-323) / SCENE_Net_Class.forward (SCENE_Net.py:465-466):
  * out = (p >= tau) as 0/1, same dtype as p. */
 int sn_threshold(const void* p, int dtype, double tau, int64_t n, void* out, void* stream);
+/* vxg_to_xyz (utils/voxelization.py:328-360): a voxel grid [d0, d1, d2] (SN_F32 / SN_F64 / SN_U8, DEVICE) as a raw point
+ * cloud: out [d0*d1*d2, 4] float64 (DEVICE, 16-byte aligned), row i = (origin + (i0, i1, i2) * voxel_size, vxg[i0, i1, i2]) in
+ * C order of the index — every voxel, as the reference does (callers select label == 1 themselves).  origin, voxel_size:
+ * HOST double[3] (the reference's defaults are (0, 0, 0) and (1, 1, 1)). */
+int sn_vxg_to_xyz(const void* vxg, int dtype, int d0, int d1, int d2, const double* origin, const double* voxel_size,
+                  double* out, void* stream);
 
 /* ======================================================================================
  * Metric state — replaces the update of the torchmetrics 0.9.0 collection the reference

@@ -218,3 +218,14 @@ class PyntCloudShim:
         vid = "V({},{},{})".format(vg["x_y_z"], [kwargs.get("size_x"), kwargs.get("size_y"), kwargs.get("size_z")], True)
         self.structures[vid] = _VoxelGridShim(vg)
         return vid
+
+
+def vxg_to_xyz(vxg, origin=None, voxel_size=None) -> np.ndarray:
+    """utils/voxelization.py:328-360: every voxel of a 3-D grid as a row (origin + index * voxel_size, value), C order
+    of the index (np.indices(shape).reshape(3, -1).T), float64."""
+    a = np.asarray(vxg)
+    origin = np.array([0, 0, 0]) if origin is None else np.asarray(origin)
+    voxel_size = np.array([1, 1, 1]) if voxel_size is None else np.asarray(voxel_size)
+    idx = np.indices(a.shape).reshape(3, -1).T
+    pts = origin + idx * voxel_size
+    return np.concatenate((pts, a.reshape(-1, 1)), axis=1).astype(np.float64)

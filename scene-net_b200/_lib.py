@@ -72,6 +72,7 @@ SIGNATURES = {
     "sn_cast_f64_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_cast_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "sn_threshold": (_i, [_vp, _i, _d, _i64, _vp, _vp]),
+    "sn_vxg_to_xyz": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sn_confusion_counts": (_i, [_vp, _i, _vp, _i, _i64, _d, _vp, _vp, _vp]),
     "sn_vox_minmax": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "sn_vox_edges": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),

@@ -327,6 +327,47 @@ extern "C" int sn_threshold(const void* p, int dtype, double tau, int64_t n, voi
     return SN_OK;
 }
 
+namespace sn {
+// vxg_to_xyz: row i of out = (origin + (i0, i1, i2) * voxel_size, vxg[i0, i1, i2]) for the C-order index i
+template <typename T>
+__global__ void __launch_bounds__(256) vxg_to_xyz_kernel(const T* __restrict__ vxg, int d1, int d2, long long n, double o0, double o1,
+                                                         double o2, double s0, double s1, double s2, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / d2;
+        const int i2 = (int)(i - r * d2), i1 = (int)(r % d1);
+        const long long i0 = r / d1;
+        // numpy: origin + index * voxel_size, two separately rounded float64 operations
+        const double2 a = make_double2(__dadd_rn(o0, __dmul_rn((double)i0, s0)), __dadd_rn(o1, __dmul_rn((double)i1, s1)));
+        const double2 b = make_double2(__dadd_rn(o2, __dmul_rn((double)i2, s2)), (double)vxg[i]);
+        reinterpret_cast<double2*>(out)[2 * i] = a;
+        reinterpret_cast<double2*>(out)[2 * i + 1] = b;
+    }
+}
+}  // namespace sn
+
+extern "C" int sn_vxg_to_xyz(const void* vxg, int dtype, int d0, int d1, int d2, const double* origin, const double* voxel_size,
+                             double* out, void* stream) {
+    if (!vxg || !out || !origin || !voxel_size || d0 < 0 || d1 < 0 || d2 < 0) return SN_ERR_BAD_ARG;
+    if ((uintptr_t)out & 15) return SN_ERR_ALIGN;
+    const long long n = (long long)d0 * d1 * d2;
+    if (n == 0) return SN_OK;
+    const int grid = sn::grid_for(n, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SN_F32)
+        sn::vxg_to_xyz_kernel<float><<<grid, 256, 0, s>>>((const float*)vxg, d1, d2, n, origin[0], origin[1], origin[2], voxel_size[0],
+                                                          voxel_size[1], voxel_size[2], out);
+    else if (dtype == SN_F64)
+        sn::vxg_to_xyz_kernel<double><<<grid, 256, 0, s>>>((const double*)vxg, d1, d2, n, origin[0], origin[1], origin[2], voxel_size[0],
+                                                           voxel_size[1], voxel_size[2], out);
+    else if (dtype == SN_U8)
+        sn::vxg_to_xyz_kernel<unsigned char><<<grid, 256, 0, s>>>((const unsigned char*)vxg, d1, d2, n, origin[0], origin[1], origin[2],
+                                                                  voxel_size[0], voxel_size[1], voxel_size[2], out);
+    else
+        return SN_ERR_BAD_ARG;
+    SN_LAUNCH_CHECK();
+    return SN_OK;
+}
+
 extern "C" int sn_fp32_peak_probe(float* sink, int iters, double* flops_out_host, void* stream) {
     if (!sink || iters < 1) return SN_ERR_BAD_ARG;
     const int blocks = sn::kNumSMs * 8, threads = 256;

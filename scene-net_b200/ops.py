@@ -498,6 +498,27 @@ def threshold(p: torch.Tensor, tau: float) -> torch.Tensor:
     return out
 
 
+def vxg_to_xyz(vxg: torch.Tensor, origin=(0.0, 0.0, 0.0), voxel_size=(1.0, 1.0, 1.0)) -> torch.Tensor:
+    """[d0*d1*d2, 4] float64 on the grid's device: (origin + index * voxel_size, value) for every voxel, C order."""
+    _need_cuda(vxg, "vxg")
+    if vxg.dim() != 3:
+        raise ValueError(f"vxg_to_xyz: a 3-D voxel grid is expected, got shape {tuple(vxg.shape)}")
+    if vxg.dtype == torch.bool:
+        vxg = vxg.to(torch.uint8)
+    if vxg.dtype not in (torch.float32, torch.float64, torch.uint8):
+        vxg = vxg.to(torch.float64)
+    vxg = vxg.contiguous()
+    o = (C.c_double * 3)(*[float(v) for v in origin])
+    vs = (C.c_double * 3)(*[float(v) for v in voxel_size])
+    out = torch.empty((vxg.numel(), 4), dtype=torch.float64, device=vxg.device)
+    if vxg.numel() == 0:
+        return out
+    with _on_device(vxg.device):
+        check(lib.sn_vxg_to_xyz(vxg.data_ptr(), _YDT[vxg.dtype], int(vxg.shape[0]), int(vxg.shape[1]), int(vxg.shape[2]),
+                                C.addressof(o), C.addressof(vs), out.data_ptr(), _stream()), "sn_vxg_to_xyz")
+    return out
+
+
 _YDT = {torch.float32: SN_F32, torch.float64: SN_F64, torch.uint8: SN_U8, torch.int32: SN_I32, torch.int64: SN_I64}
 
 

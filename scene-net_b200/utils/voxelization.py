@@ -84,3 +84,16 @@ def prob_to_label(voxelgrid: Union[torch.Tensor, np.ndarray], tau: float) -> Uni
     a = np.asarray(voxelgrid)
     t = ops.threshold(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(_device()), tau)
     return t.cpu().numpy().astype(a.dtype)
+
+
+def vxg_to_xyz(vxg: Union[torch.Tensor, np.ndarray], origin=None, voxel_size=None) -> np.ndarray:
+    """utils/voxelization.py:328-360 of the reference: a voxel grid as a raw point cloud, (N, 4) numpy float64 with
+    N = vxg.numel(): rows (origin + index * voxel_size, vxg[index]) for EVERY voxel in C order (callers keep the rows with
+    label 1).  The reference loops over the voxels in Python (one tensor index per voxel: ~3 s for a 64^3 grid); here
+    one kernel writes the rows.  Defaults as there: origin (0, 0, 0), voxel_size (1, 1, 1)."""
+    origin = (0.0, 0.0, 0.0) if origin is None else np.asarray(origin, dtype=np.float64).reshape(3)
+    voxel_size = (1.0, 1.0, 1.0) if voxel_size is None else np.asarray(voxel_size, dtype=np.float64).reshape(3)
+    t = vxg if isinstance(vxg, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vxg))
+    if not t.is_cuda:
+        t = t.to(_device())
+    return ops.vxg_to_xyz(t, origin, voxel_size).cpu().numpy()

@@ -184,3 +184,29 @@ def test_properties_at_10m_points():
         o2 = voxel_ops.voxelize_clouds(pts, None, grid, labels, [15], want=("keep_count", "max_label"))
         assert torch.equal(o1["count"], o2["count"]) and torch.equal(o1["max_label"], o2["max_label"])
         assert float(o1["max_label"].max()) == 19.0
+
+
+def test_vxg_to_xyz_vs_reference_outputs_and_oracle():
+    """vxg_to_xyz (utils/voxelization.py:328-360): bit-exact against the reference's own outputs on the committed fixtures and
+    against the oracle on a 64^3 prediction-shaped grid with UTM origin (every voxel, C order, float64)."""
+    import scenenet_b200 as sb
+    from oracle import voxel_oracle as vo
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vxg_to_xyz.npz"))
+    for name in sorted({k.split(".")[0] for k in gold.files}):
+        origin = gold[f"{name}.origin"] if gold[f"{name}.origin"].size else None
+        size = gold[f"{name}.size"] if gold[f"{name}.size"].size else None
+        vxg = gold[f"{name}.vxg"]
+        for arg in (vxg, torch.from_numpy(vxg), torch.from_numpy(vxg).cuda()):
+            out = sb.voxelization.vxg_to_xyz(arg, origin, size)
+            assert isinstance(out, np.ndarray) and out.dtype == np.float64
+            assert out.shape == gold[f"{name}.out"].shape and np.array_equal(out, gold[f"{name}.out"]), name
+    rng = np.random.default_rng(3)
+    grid = (rng.random((64, 64, 64)) < 0.02).astype(np.float64)
+    origin, size = np.array([544850.123, 4634550.456, 160.789]), np.array([0.46875, 0.46875, 0.7])
+    out = sb.voxelization.vxg_to_xyz(grid, origin, size)
+    assert np.array_equal(out, vo.vxg_to_xyz(grid, origin, size))
+    # the rows a caller keeps: label == 1
+    assert int((out[:, 3] == 1.0).sum()) == int(grid.sum())
+    with pytest.raises(ValueError):
+        sb.voxelization.vxg_to_xyz(np.zeros((2, 3, 4, 5)))
+    assert sb.voxelization.vxg_to_xyz(np.zeros((0, 3, 4))).shape == (0, 4)

@@ -114,3 +114,15 @@ def test_live_reference_reg_on_voxel_other_samples():
         pts, labels = npy[:, :3], npy[:, 3]
         ref = Vox.reg_on_voxel(pts, labels, [15], voxelgrid_dims=(32, 32, 32))
         assert np.array_equal(vo.reg_on_voxel(pts, labels, [15], (32, 32, 32)), ref)
+
+
+def test_vxg_to_xyz_restatement_equals_reference_outputs():
+    """oracle.voxel_oracle.vxg_to_xyz against outputs of the reference's own function (oracle/make_golden_vxg.py)."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vxg_to_xyz.npz"))
+    names = sorted({k.split(".")[0] for k in gold.files})
+    assert names == ["f32_origin_size", "f64_default", "u8_int_origin"]
+    for name in names:
+        origin = gold[f"{name}.origin"] if gold[f"{name}.origin"].size else None
+        size = gold[f"{name}.size"] if gold[f"{name}.size"].size else None
+        out = vo.vxg_to_xyz(gold[f"{name}.vxg"], origin, size)
+        assert out.shape == gold[f"{name}.out"].shape and np.array_equal(out, gold[f"{name}.out"]), name
