@@ -128,7 +128,8 @@ class TS40KDeviceLoader:
 
     def __init__(self, sources, batch_size: int, keep_labels: Sequence[float] = (POWER_LINE_SUPPORT_TOWER,),
                  vxg_size: Sequence[int] = (64, 64, 64), device: Optional[torch.device] = None, dtype: torch.dtype = torch.float64,
-                 shuffle: bool = False, drop_last: bool = False, seed: Optional[int] = None, io_threads: Optional[int] = None):
+                 shuffle: bool = False, drop_last: bool = False, seed: Optional[int] = None, io_threads: Optional[int] = None,
+                 pin_sources_bytes: int = 8 << 30):
         if isinstance(sources, TS40K):
             sources = [sources.path_of(i) for i in range(len(sources))]
         self.sources: List[Source] = list(sources)
@@ -148,6 +149,52 @@ class TS40KDeviceLoader:
         self._staging = [None, None]  # two pinned [cap, 4] float64 buffers, reused across batches
         self._uploaded = [None, None]  # the event of the last H2D copy that READ each pinned slot
         self._copy_stream = torch.cuda.Stream(device=self.device)
+        # in-memory samples ([N, 4] float64, C order) are page-locked IN PLACE (cudaHostRegister, up to pin_sources_bytes):
+        # their rows then go to the device straight from the arrays, one asynchronous copy per cloud, and the staging
+        # memcpy — what bounded the loader at 12.8 k clouds/s, half the PCIe rate — disappears
+        self._registered = {}  # id(array) -> (array, data pointer)
+        self._pin_sources(int(pin_sources_bytes))
+
+    def _pin_sources(self, budget: int):
+        if budget <= 0:
+            return
+        rt = torch.cuda.cudart()
+        seen = set()
+        for a in self.sources:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.shape[1] == 4 and a.flags.c_contiguous
+                    and a.shape[0] > 0):
+                continue
+            if id(a) in seen:
+                continue
+            seen.add(id(a))
+            if a.nbytes > budget:
+                continue
+            ptr = a.ctypes.data
+            try:
+                err = rt.cudaHostRegister(ptr, a.nbytes, 0)
+            except Exception:  # noqa: BLE001  (no such binding / not permitted: the staging path serves the sample)
+                return
+            if int(err) != 0:
+                return
+            budget -= a.nbytes
+            self._registered[id(a)] = (a, ptr)
+
+    def close(self):
+        """release the page locks taken on in-memory samples"""
+        if self._registered:
+            rt = torch.cuda.cudart()
+            for _, ptr in self._registered.values():
+                try:
+                    rt.cudaHostUnregister(ptr)
+                except Exception:  # noqa: BLE001
+                    pass
+            self._registered = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def __len__(self) -> int:
         n = len(self.sources)
@@ -179,6 +226,12 @@ class TS40KDeviceLoader:
             raise
 
     def _stage(self, idxs: Sequence[int], slot: int):
+        if self._registered and all(id(self.sources[i]) in self._registered for i in idxs):
+            # every sample of the batch is page-locked in place: nothing to stage
+            arrays = [self.sources[i] for i in idxs]
+            offs = np.zeros(len(arrays) + 1, dtype=np.int64)
+            np.cumsum([a.shape[0] for a in arrays], out=offs[1:])
+            return arrays, torch.from_numpy(offs).pin_memory(), -1
         arrays = list(self._pool.map(self._read_one, idxs))
         counts = [a.shape[0] for a in arrays]
         total = sum(counts)
@@ -207,11 +260,18 @@ class TS40KDeviceLoader:
     def _upload(self, staged):
         rows, offs, slot = staged
         with torch.cuda.stream(self._copy_stream):
-            d_rows = rows.to(self.device, non_blocking=True)  # one cudaMemcpyAsync for the whole batch
+            if slot < 0:
+                # page-locked samples: one cudaMemcpyAsync per cloud, straight from the arrays into the batch buffer
+                d_rows = torch.empty((int(offs[-1]), 4), dtype=torch.float64, device=self.device)
+                for i, a in enumerate(rows):
+                    d_rows[int(offs[i]):int(offs[i + 1])].copy_(torch.from_numpy(a), non_blocking=True)
+            else:
+                d_rows = rows.to(self.device, non_blocking=True)  # one cudaMemcpyAsync for the whole batch
             d_offs = offs.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._uploaded[slot] = ev
+        if slot >= 0:
+            self._uploaded[slot] = ev
         return d_rows, d_offs, ev
 
     def _voxelize(self, uploaded):

@@ -78,3 +78,33 @@ def test_loader_golden_sample_575_and_replacement_of_bad_samples():
     for j in range(3):  # the empty sample was replaced by a readable one (all sources but it are sample_575)
         assert np.array_equal(y[j, 0].cpu().numpy(), want_y)
         assert np.array_equal(x[j, 0].cpu().numpy(), want_x) and int(x[j].sum()) == 4247  # SURVEY §8c KAT
+
+
+def test_in_memory_samples_are_page_locked_in_place():
+    """[N, 4] float64 arrays held in memory are registered with the driver once and copied to the device straight from
+    the arrays: the batches equal those of the staging path (pin_sources_bytes=0) and of the oracle, twice over (two epochs),
+    and a mixed list (one float32 array: not registrable) falls back to staging."""
+    import scenenet_b200 as sb
+    rng = np.random.default_rng(11)
+    clouds = [_cloud(rng, n) for n in (5000, 33, 12000, 900, 64, 7000)]
+    grid = (32, 32, 32)
+    direct = sb.TS40KDeviceLoader(clouds, batch_size=4, vxg_size=grid, device=DEV)
+    staged = sb.TS40KDeviceLoader(clouds, batch_size=4, vxg_size=grid, device=DEV, pin_sources_bytes=0)
+    assert not staged._registered
+    if not direct._registered:
+        pytest.skip("cudaHostRegister is not available through torch.cuda.cudart() on this box")
+    assert len(direct._registered) == len(clouds)
+    for _ in range(2):
+        seen = 0
+        for (x, y), (xs, ys) in zip(direct, staged):
+            assert torch.equal(x, xs) and torch.equal(y, ys)
+            for j in range(x.shape[0]):
+                wx, wy = _oracle_xy(clouds[seen], grid)
+                assert np.array_equal(x[j, 0].cpu().numpy(), wx) and np.array_equal(y[j, 0].cpu().numpy(), wy)
+                seen += 1
+        assert seen == len(clouds)
+    direct.close()
+    assert not direct._registered
+    mixed = sb.TS40KDeviceLoader(clouds[:3] + [clouds[3].astype(np.float32)], batch_size=4, vxg_size=grid, device=DEV)
+    (x, y), = list(mixed)
+    assert torch.equal(x[:3], next(iter(staged))[0][:3])
