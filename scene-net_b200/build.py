@@ -76,7 +76,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(log)
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+        # --no-undefined: a declaration that no longer matches its definition must fail HERE, not as an unresolved symbol
+        # when the library is loaded on the GPU box
+        cmd = [_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

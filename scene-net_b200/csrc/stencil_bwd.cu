@@ -36,7 +36,7 @@ int stencil_tapgrad_generic(const BwdParams& p, int ky, double* W, cudaStream_t 
 int64_t tapgrad_sparse_ws(int B, int Z, int X, int Y, int kz, int kx, int ky);
 int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long long* nnz, unsigned long long nnz_max,
                           int B, int Z, int X, int Y, int kz, int kx, int ky, void* ws, int64_t ws_bytes, int* rows_out,
-                          double* W, unsigned long long* ticket, cudaStream_t stream);
+                          double* W, unsigned long long* ticket, cudaStream_t stream, const unsigned long long* state);
 
 // G0 = dpred * (1 - pred^2) * [pred > 0]: 4 voxels per thread, all loads issued before use
 template <typename TP, typename TD>
@@ -208,11 +208,13 @@ extern "C" int sn_scenenet_tapgrad(const float* x, const float* g0, const unsign
     if (run_dense && !fast_ky(ky)) return sn::stencil_tapgrad_generic(p, ky, W, s);
     if (!ws) return SN_ERR_WORKSPACE;
     int rows = 0, rows_sparse = 0, TP = (T + 31) & ~31, rc = SN_OK;
-    // with a count buffer from sn_grid_prepare the second word is a ticket counter (zeroed by that call): the CTA
-    // that finishes last sums the partial rows itself; without it a separate kernel does
-    unsigned long long* ticket = nnz ? const_cast<unsigned long long*>(nnz) + 1 : nullptr;
+    // The partial rows are summed by a separate kernel.  (Round 1 let the CTA that finishes last sum them — a ticket counter
+    // in the state buffer's second word, last_cta_row_sum — to save a launch: one CTA reading 148 x T doubles is slower than
+    // T / 32 CTAs after a 1 us kernel boundary: config 2 step 0.1389 -> 0.1359 ms without it, 9^3 taps -10 us, 15^3 -57 us;
+    // profiles/r2_notes.md.  The kernels keep the ticket parameter; the word stays reserved.)
+    unsigned long long* ticket = nullptr;
     if (run_sparse) {
-        rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, W, ticket, s);
+        rc = sn::tapgrad_sparse_launch(x, g0, gate, nnz_max, B, Z, X, Y, kz, kx, ky, ws, ws_bytes, &rows_sparse, W, ticket, s, nnz);
         if (rc) return rc;
     }
     if (run_dense) {

@@ -42,13 +42,15 @@ struct SpParams {
     unsigned long long* ticket;      // device counter zeroed by sn_grid_prepare (NULL: a separate kernel sums the rows)
     const unsigned long long* nnz;   // device; NULL = always run
     unsigned long long nnz_max;      // run iff *nnz <= nnz_max
+    const unsigned long long* state; // grid state buffer of x (sn_grid_prepare), or NULL
+    const unsigned* mask;            // its occupancy bits when the tiles are made of whole mask words, else NULL
     int B, Z, X, Y, kz, kx, ky;
     int IX, IY, lgIX, lgIY;          // interior tile (z extent kRZ); powers of two
     int HZ, HX, WS;                  // G0 box
     int tiles_z, tiles_x, tiles_y, ntiles;
     int prz, prx, pra;               // box start = tile origin - (prz, prx, pra); pra = round4(right pad y)
     int ybase;                       // y offset of voxel (.,.,0) + left pad inside a box row
-    int nchunks, S, nactive, nstage, use_tma, TP;
+    int nchunks, S, nactive, nstage, nstage_bits, use_tma, TP;
 };
 
 __device__ __forceinline__ void sp_decode_tile(int tile, const SpParams& p, int& b, int& z0, int& x0, int& y0) {
@@ -73,9 +75,15 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int xi_floats = kRZ * p.IX * p.IY;
     const int halo_floats = p.HZ * p.HX * p.WS;
-    const int stage_floats = xi_floats + ((halo_floats + 31) & ~31);
+    // Binary grids (every non-zero voxel is 1: state[4] == 0) with a state buffer: the non-zero voxels come from the
+    // occupancy BITS — the x tile is neither staged nor scanned, and a stage is the G0 box alone (one more stage in flight)
+    const bool bits = p.mask != nullptr && p.state[4] == 0ull;
+    const int xoff = bits ? 0 : xi_floats;  // the G0 box inside a stage
+    const int stage_floats = xoff + ((halo_floats + 31) & ~31);
+    const int nstage = bits ? p.nstage_bits : p.nstage;
     float* s0 = reinterpret_cast<float*>(smem_raw);
-    const int data_floats = max(p.nstage * stage_floats, kSpWarps * kSpChunk * 2);
+    const int data_floats = max(max(p.nstage * (xi_floats + ((halo_floats + 31) & ~31)), p.nstage_bits * ((halo_floats + 31) & ~31)),
+                                kSpWarps * kSpChunk * 2);
     uint64_t* full = reinterpret_cast<uint64_t*>(s0 + data_floats);  // [kSpMaxStages]
     uint64_t* empty = full + kSpMaxStages;
 
@@ -86,7 +94,7 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
 
     if (p.use_tma) {
         if (tid == 0) {
-            for (int i = 0; i < p.nstage; ++i) {
+            for (int i = 0; i < kSpMaxStages; ++i) {
                 mbar_init(&full[i], 1);
                 mbar_init(&empty[i], p.nactive);
             }
@@ -142,6 +150,67 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
         }
     };
 
+    // occupancy bits: slice s takes the words s, s + S, ... of the tile (32 voxels of one row each); lane l holds word
+    // s + S * l, loaded one tile ahead; the tile coordinates advance by G tiles per step without divisions
+    const int widx = s + p.S * lane;
+    const bool wmine = compute && widx < (xi_floats >> 5);
+    const int we0 = widx << 5;  // tile-linear index of the word's first voxel
+    const int wy = we0 & mY, wx = (we0 >> p.lgIY) & mX, wz = we0 >> lgXY;
+    int cty, ctx, ctz, cb;     // tile of the next word load (ty, tx, tz, b)
+    int gty, gtx, gtz, gb;     // G tiles as (ty, tx, tz, b) steps
+    {
+        int t = blockIdx.x;
+        cty = t % p.tiles_y; t /= p.tiles_y; ctx = t % p.tiles_x; t /= p.tiles_x; ctz = t % p.tiles_z; cb = t / p.tiles_z;
+        t = G;
+        gty = t % p.tiles_y; t /= p.tiles_y; gtx = t % p.tiles_x; t /= p.tiles_x; gtz = t % p.tiles_z; gb = t / p.tiles_z;
+    }
+    auto load_word = [&]() -> unsigned {  // the word of tile (cty, ctx, ctz, cb); then advance by G tiles
+        unsigned w = 0u;
+        const int gz = ctz * kRZ + wz, gx = ctx * p.IX + wx, gy = cty * p.IY + wy;
+        if (wmine && cb < p.B && gz < p.Z && gx < p.X && gy < p.Y)
+            w = __ldg(p.mask + (((((long long)cb * p.Z + gz) * p.X + gx) * p.Y + gy) >> 5));
+        cty += gty;
+        int carry = cty >= p.tiles_y ? 1 : 0;
+        cty -= carry * p.tiles_y;
+        ctx += gtx + carry;
+        carry = ctx >= p.tiles_x ? 1 : 0;
+        ctx -= carry * p.tiles_x;
+        ctz += gtz + carry;
+        carry = ctz >= p.tiles_z ? 1 : 0;
+        ctz -= carry * p.tiles_z;
+        cb += gb + carry;
+        return w;
+    };
+    auto scan_words = [&](unsigned word, const float* sgp) {
+        const uint32_t sg = smem_u32(sgp);
+        unsigned have = __ballot_sync(0xffffffffu, word != 0u);
+        while (have) {
+            const int l = __ffs(have) - 1;
+            have &= have - 1u;
+            unsigned w = __shfl_sync(0xffffffffu, word, l);
+            const int e0 = (s + p.S * l) << 5;
+            const uint32_t gp0 = sg + 4u * (uint32_t)((e0 >> lgXY) * zs + ((e0 >> p.lgIY) & mX) * p.WS + (e0 & mY));
+            while (w) {
+                const uint32_t gp = gp0 + 4u * (uint32_t)(__ffs(w) - 1);
+                w &= w - 1u;
+#pragma unroll
+                for (int i = 0; i < kSpNI; ++i) {
+                    float g;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(gp + noff[i]));
+                    acc[i] += g;  // x = 1
+                }
+                if (++pending == kSpFlush) {
+#pragma unroll
+                    for (int i = 0; i < kSpNI; ++i) {
+                        accd[i] += (double)acc[i];
+                        acc[i] = 0.f;
+                    }
+                    pending = 0;
+                }
+            }
+        }
+    };
+
     auto scan_tile = [&](const float* sx, const float* sgp) {
         const uint32_t sg = smem_u32(sgp);
         const float4* sx4 = reinterpret_cast<const float4*>(sx);
@@ -163,26 +232,32 @@ tapgrad_sparse_kernel(const SpParams p, const __grid_constant__ CUtensorMap xmap
             if (lane == 0) {
                 int k = 0;
                 for (int tile = blockIdx.x; tile < p.ntiles; tile += G, ++k) {
-                    const int st = k % p.nstage;
-                    if (k >= p.nstage) {
-                        mbar_wait(&empty[st], (uint32_t)(k / p.nstage - 1) & 1u);
+                    const int st = k % nstage;
+                    if (k >= nstage) {
+                        mbar_wait(&empty[st], (uint32_t)(k / nstage - 1) & 1u);
                         fence_proxy_async();
                     }
                     int b, z0, x0, y0;
                     sp_decode_tile(tile, p, b, z0, x0, y0);
                     float* sx = s0 + st * stage_floats;
-                    mbar_arrive_expect_tx(&full[st], (uint32_t)(xi_floats + halo_floats) * 4u);
-                    tma_load_4d(sx, &xmap, &full[st], y0, x0, z0, b);
-                    tma_load_4d(sx + xi_floats, &gmap, &full[st], y0 - p.pra, x0 - p.prx, z0 - p.prz, b);
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)(xoff + halo_floats) * 4u);
+                    if (!bits) tma_load_4d(sx, &xmap, &full[st], y0, x0, z0, b);
+                    tma_load_4d(sx + xoff, &gmap, &full[st], y0 - p.pra, x0 - p.prx, z0 - p.prz, b);
                 }
             }
         } else if (compute) {
             int k = 0;
+            unsigned wnext = bits ? load_word() : 0u;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += G, ++k) {
-                const int st = k % p.nstage;
-                mbar_wait(&full[st], (uint32_t)(k / p.nstage) & 1u);
+                const int st = k % nstage;
+                const unsigned word = wnext;
+                if (bits) wnext = load_word();
+                mbar_wait(&full[st], (uint32_t)(k / nstage) & 1u);
                 const float* sx = s0 + st * stage_floats;
-                scan_tile(sx, sx + xi_floats);
+                if (bits)
+                    scan_words(word, sx);
+                else
+                    scan_tile(sx, sx + xi_floats);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[st]);
             }
@@ -316,8 +391,12 @@ static bool plan_sparse(int B, int Z, int X, int Y, int kz, int kx, int ky, SpPa
     int ns = (int)((227 * 1024 - extra) / stage);
     if (ns < 1) return false;
     p.nstage = ns > kSpMaxStages ? kSpMaxStages : ns;
+    const size_t stage_bits = (size_t)((p.HZ * p.HX * p.WS + 31) & ~31) * 4;  // binary grids: the G0 box alone
+    int nsb = (int)((227 * 1024 - extra) / stage_bits);
+    p.nstage_bits = nsb > kSpMaxStages ? kSpMaxStages : nsb;
     const size_t red = (size_t)kSpWarps * kSpChunk * 8;
-    smem = (p.nstage * stage > red ? p.nstage * stage : red) + extra;
+    size_t data = p.nstage * stage > p.nstage_bits * stage_bits ? p.nstage * stage : p.nstage_bits * stage_bits;
+    smem = (data > red ? data : red) + extra;
     return true;
 }
 
@@ -331,7 +410,7 @@ int64_t tapgrad_sparse_ws(int B, int Z, int X, int Y, int kz, int kx, int ky) {
 // rows_out = partial rows written (0 when the sparse kernel is not applicable)
 int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long long* nnz, unsigned long long nnz_max,
                           int B, int Z, int X, int Y, int kz, int kx, int ky, void* ws, int64_t ws_bytes, int* rows_out,
-                          double* W, unsigned long long* ticket, cudaStream_t stream) {
+                          double* W, unsigned long long* ticket, cudaStream_t stream, const unsigned long long* state) {
     SpParams p{};
     size_t smem;
     *rows_out = 0;
@@ -345,6 +424,10 @@ int tapgrad_sparse_launch(const float* x, const float* g0, const unsigned long l
     const bool okg = make_grid_tmap(&gmap, g0, B, Z, X, Y, p.HZ, p.HX, p.WS);
     p.use_tma = (okx && okg) ? 1 : 0;
     if (!p.use_tma) p.nstage = 1;
+    // occupancy bits instead of the x tile: tiles made of whole mask words, at most 32 words per slice, TMA path
+    p.state = state;
+    const bool words_ok = state && p.use_tma && (Y & 31) == 0 && (p.IY & 31) == 0 && (kRZ * p.IX * p.IY >> 5) <= 32 * p.S;
+    p.mask = words_ok ? reinterpret_cast<const unsigned*>(state + SN_STATE_WORDS) : nullptr;
     cudaError_t e = cudaFuncSetAttribute(tapgrad_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
     tapgrad_sparse_kernel<<<grid, kSpThreads, smem, stream>>>(p, xmap, gmap);

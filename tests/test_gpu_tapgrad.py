@@ -79,8 +79,9 @@ def test_device_side_selection(density, expect_sparse):
         assert int(nnz[0]) == int((xin != 0).sum())
         assert x32.dtype == torch.float32 and torch.equal(x32, xin.to(torch.float32))
         Wa = ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_AUTO)
-        We = ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_SPARSE if expect_sparse else SN_TAPGRAD_DENSE)
-        Wo = ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_DENSE if expect_sparse else SN_TAPGRAD_SPARSE)
+        # (forced runs with the same state buffer: binary grids take their voxels from its occupancy bits, another order)
+        We = ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_SPARSE if expect_sparse else SN_TAPGRAD_DENSE)
+        Wo = ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_DENSE if expect_sparse else SN_TAPGRAD_SPARSE)
         assert torch.equal(Wa, We)
         assert torch.allclose(Wa, Wo, rtol=1e-4, atol=1e-4 * float(Wo.abs().max()))
         # the same count buffer serves a second backward (the last CTA resets its ticket)
@@ -149,3 +150,6 @@ def test_bwd_entry_point_equals_g0_plus_tapgrad(B, grid, ks, density, binary, dt
     # without a state buffer: the two-kernel path
     assert torch.equal(ops.scenenet_bwd(x32, pred, dpred, ks, mode=SN_TAPGRAD_SPARSE), ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_SPARSE))
     assert torch.equal(ops.tapgrad(x32, g0, ks, nnz=state, mode=SN_TAPGRAD_SPARSE), Wf)
+    # binary grids with a state buffer are walked through the occupancy bits (no x tile): same sum, another order
+    Wx = ops.tapgrad(x32, g0, ks, mode=SN_TAPGRAD_SPARSE)
+    assert bool(((Wx - ref).abs() <= tol).all()) and (binary or torch.equal(Wx, Wf))
