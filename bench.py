@@ -569,11 +569,11 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms)
     value = B_PER_GPU * world * args.steps / (total_ms * 1e-3)
-    # synth, prepare (cast + non-zero count + occupancy bits), forward, g0, tap gradient (its last CTA sums the rows),
-    # param_grads (which also exchanges the gradients over NVLink when N > 1); specialised capture: no gated-out launches
-    kernels_per_step = 6 + (1 if (world > 1 and not getattr(model.grad_sync_group, "fused_with_param_grads", False)) else 0)
+    # synthesis, prepare (cast + non-zero count + occupancy bits), forward, g0, tap gradient, row sum, parameter Jacobian^T
+    # (which also exchanges the gradients over NVLink when N > 1); specialised capture: no gated-out
+    # launches.  Replayed graph nodes: the library's host-side counter saw them once, at capture (GraphedStep.kernels_per_replay)
     if graphs is not None:
-        launches = kernels_per_step * args.steps  # replayed graph nodes: the library's host-side counter does not see them
+        launches = sum(graphs[(args.warmup + i) % n_sets].kernels_per_replay for i in range(args.steps))
 
     # eager module path (what a drop-in user gets without graph capture), a few steps, for the record
     for i in range(3):

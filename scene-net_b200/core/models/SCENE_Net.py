@@ -35,6 +35,20 @@ def _side_stream(device) -> torch.cuda.Stream:
     return st
 
 
+_HI_STREAMS = {}
+
+
+def _hi_stream(device) -> torch.cuda.Stream:
+    """a HIGH-priority stream for the one-CTA synthesis kernels: their CTA is placed as soon as a slot frees up instead of
+    queueing behind the thousands of CTAs of the grid preparation that runs beside them"""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _HI_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device, priority=-1)
+        _HI_STREAMS[key] = st
+    return st
+
+
 def _finish_backward(ctx, W):
     """tap gradient -> parameter gradients (+ the gradient all-reduce), shared by the two autograd functions"""
     x32, pred, K, lam, snap, nnz = ctx.saved_tensors[:6]
@@ -63,10 +77,12 @@ class _ObserverLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, spec, crit_spec, write_last, grad_scale, sync_group, path_modes, *params):
         cur = ops.current_stream_obj(x.device)
-        side = _side_stream(x.device)
+        side, hi = _side_stream(x.device), _hi_stream(x.device)
+        hi.wait_stream(cur)
+        K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last, stream=hi)
         x32, nnz = ops.prepare(x.detach(), stream=side)
-        K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         cur.wait_stream(side)
+        cur.wait_stream(hi)
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz,
                                 mode=path_modes[0])
         loss, coef, p, t = ops.criterion_fwd(pred, y.detach(), crit_spec)
@@ -79,7 +95,7 @@ class _ObserverLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g_pred):
-        x32, p, K, lam, snap, nnz, t, coef = ctx.saved_tensors
+        x32, p, K, lam, snap, nnz, t, coef = ctx.saved_tensors[:8]
         g0 = ops.criterion_bwd(p, t, coef, ctx.crit_spec, grad_out=g_loss, as_g0=True)
         W = ops.tapgrad(x32, g0, ctx.spec.kernel_size, nnz=nnz, mode=ctx.bwd_mode)
         d = _finish_backward(ctx, W)
@@ -100,10 +116,12 @@ class _ObserverFunction(torch.autograd.Function):
             K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
         else:
             cur = ops.current_stream_obj(x.device)
-            side = _side_stream(x.device)
+            side, hi = _side_stream(x.device), _hi_stream(x.device)
+            hi.wait_stream(cur)
+            K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last, stream=hi)
             x32, nnz = ops.prepare(x.detach(), stream=side)  # buffers belong to the current stream, the pass runs on `side`
-            K, lam, Kstar, snap = ops.synth_fwd(spec, [p.detach() for p in params], write_last_lambda=write_last)
             cur.wait_stream(side)
+            cur.wait_stream(hi)
         # pred comes back in the caller's dtype; byte/bool occupancy inputs (an extension) give float32
         pred = ops.scenenet_fwd(x32, Kstar, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32, nnz,
                                 mode=path_modes[0])
@@ -116,7 +134,7 @@ class _ObserverFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpred):
-        x32, pred, K, lam, snap, nnz = ctx.saved_tensors
+        x32, pred, K, lam, snap, nnz = ctx.saved_tensors[:6]
         W = ops.scenenet_bwd(x32, pred, dpred, ctx.spec.kernel_size, nnz, mode=ctx.bwd_mode)
         d = _finish_backward(ctx, W)
         unused = ctx.spec.unused

@@ -65,8 +65,12 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         for p in self.params:
             p.grad = None
+        from . import _lib
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self._step()
+        #: kernels of this library inside the captured step (the library counts its launches; a replay re-issues these)
+        self.kernels_per_replay = _lib.launch_count() - n0
 
     def _step(self):
         if self.x_host is not None:

@@ -156,8 +156,10 @@ def unused_cone_params(kind: int, hc: int, kz: int, base: int) -> set:
 
 
 # ------------------------------------------------------------------------------- synthesis
-def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lambda: bool = False):
-    """-> (K [G,kz,kx,ky] f32, lambda_eff [G] f32 | None, Kstar [kz,kx,ky] f32 | None, snapshot [n] f32)"""
+def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lambda: bool = False,
+              stream: Optional[torch.cuda.Stream] = None):
+    """-> (K [G,kz,kx,ky] f32, lambda_eff [G] f32 | None, Kstar [kz,kx,ky] f32 | None, snapshot [n] f32)
+    stream: launch on this stream (the caller orders it against the current one); the outputs belong to the current stream"""
     d = spec.desc()
     if len(params) != d.n_param_ptrs:
         raise ValueError(f"expected {d.n_param_ptrs} parameter tensors, got {len(params)}")
@@ -173,7 +175,8 @@ def synth_fwd(spec: ObserverSpec, params: Sequence[torch.Tensor], write_last_lam
     snap = buf[n_k + n_ks + n_l:]
     with _on_device(dev):
         check(lib.sn_geneo_synth_fwd(C.byref(d), _ptr_array(params), K.data_ptr(), _ptr(lam), _ptr(Kstar),
-                                     snap.data_ptr(), int(write_last_lambda), _stream()), "sn_geneo_synth_fwd")
+                                     snap.data_ptr(), int(write_last_lambda), _stream() if stream is None else stream.cuda_stream),
+              "sn_geneo_synth_fwd")
     return K, lam, Kstar, snap
 
 
