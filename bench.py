@@ -872,7 +872,11 @@ def main():
             "bwd_tapgrad_dense": {"us": t_tap * 1e6, "tflops": fl / t_tap / 1e12, "frac": fl / t_tap / 1e12 / peak_tf},
             "bwd_tapgrad_occupancy_driven": {"us": t_tap_sp * 1e6, "us_auto_selected": t_tap_auto * 1e6, "bound": "hbm",
                                              "GBps": V * 8 / t_tap_sp / 1e9, "hbm_frac": V * 8 / t_tap_sp / 1e9 / hbm_gbs,
-                                             "note": "x + G0 read once (8 B/voxel); skips the 98.4 % zero voxels, so the FP32 "
+                                             "with_state_buffer": {"us": t_tap_auto * 1e6, "GBps": V * 4.125 / t_tap_auto / 1e9,
+                                                                   "hbm_frac": V * 4.125 / t_tap_auto / 1e9 / hbm_gbs,
+                                                                   "note": "binary grids with the grid state (what the step runs): voxels from "
+                                                                           "the occupancy bits, G0 4 B + 1 bit per voxel, + the row-sum kernel"},
+                                             "note": "without the state buffer: x + G0 read once (8 B/voxel), + the row-sum kernel; skips the 98.4 % zero voxels, so the FP32 "
                                                      "roofline of the dense formulation does not apply"},
             "g0_pass": {"us": t_g0 * 1e6, "GBps": g0_bytes / t_g0 / 1e9, "hbm_frac": g0_bytes / t_g0 / 1e9 / hbm_gbs},
             "prepare_pass": {"us": t_cast * 1e6, "GBps": V * (esz + (4 if esz == 8 else 0)) / t_cast / 1e9,

@@ -159,7 +159,7 @@ int sn_scenenet_fwd_multi(const float* x, const unsigned long long* nnz, int mod
  * the relu/tanh/convex-combination backward of SCENE_Net.py:325-337.
  *   G0 = dpred * (1 - pred^2) * [pred > 0];   W[t] = sum_{b,v} G0[b,v] * xpad[b, v + t]
  *   x [B,1,Z,X,Y] float32, pred / dpred in pred_dtype / dpred_dtype, W [T] float64 out.
- *   nnz: DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count at [0], ticket at [1]), or NULL.
+ *   nnz: DEVICE pointer to the grid state buffer of x written by sn_grid_prepare (count at [0], occupancy bits behind the counters), or NULL.
  *        Voxel grids of point clouds are ~98 % empty: when nnz is given, an occupancy-driven
  *        kernel (cost proportional to the occupied voxels) and the dense stencil are both enqueued and the
  *        count selects ON THE DEVICE which of them does the work (sparse up to 10 % occupancy; no host
@@ -247,8 +247,8 @@ int sn_param_penalty(const float* const* param_ptrs_host, const int32_t* role_ho
 /* Grid preparation, one HBM pass: x (SN_F64 as handed over by the reference's ToTensor, torch_transforms.py:13;
  * SN_U8 occupancy bytes; SN_F32) -> float32 copy x32 for the TMA-fed stencils (SN_F32: x32 must be NULL or x,
  * nothing is copied) and the grid STATE buffer `nnz` the forward / backward take:
- *   SN_STATE_WORDS uint64 counters — [0] number of non-zero voxels, [1] ticket counter the tap-gradient kernels use to let
- *   their last CTA sum the partial rows, [2] number of 32-voxel mask words with >= 8 voxels occupied (how clustered the
+ *   SN_STATE_WORDS uint64 counters — [0] number of non-zero voxels, [1] reserved (a ticket counter of the tap-gradient
+ *   kernels up to ABI v4.0; the partial rows are summed by a kernel of their own now), [2] number of 32-voxel mask words with >= 8 voxels occupied (how clustered the
  *   grid is), [3] number of tiles the occupancy-driven forward handed to the dense stencil, [4] number of non-zero voxels
  *   whose value is not 1 (0 <=> an occupancy grid: the forward then takes its values from the mask bits), [5] tile
  *   counter of the occupancy-driven forward (dynamic tile scheduling), [6] CTA-done counter of the dense stencil's
@@ -344,8 +344,9 @@ int sn_vox_finalize(const int32_t* count, const int32_t* keep_count, int n_cloud
  * Multi-GPU: all-reduce (sum) of the parameter-gradient payload over NVLink peer memory.
  * Replaces the gradient all-reduce Lightning's implicit DDP performs for the reference
  * (scripts/main.py:224-236) — 11..96 floats per step, pure latency — by ONE single-CTA kernel:
- * every rank stores its payload into every peer's exchange buffer, raises a flag, waits for
- * the peers' flags in its own buffer and adds the payloads in rank order (bit-identical
+ * every rank stores its payload into every peer's exchange buffer as 8-byte words {value, call number} (a word carries its
+ * own flag: no fence, one NVLink traversal), polls the words of the peers' slots in its own buffer and adds the payloads in
+ * rank order (bit-identical
  * result on all ranks, deterministic).
  *   data            [n] float32 DEVICE, in place (n <= SN_MAX_PARAM_PTRS)
  *   peer_bufs_host  HOST array of `world` DEVICE pointers: entry w = rank w's exchange buffer of

@@ -4,13 +4,16 @@
 //
 // Every rank owns an exchange buffer in peer-mapped memory (allocated and rendezvoused by the host through torch's
 // symmetric memory, which hands us one device pointer per rank).  Warp w pushes this rank's payload into rank w's
-// buffer with plain stores over NVLink, fences, and raises a flag there; then it waits for rank w's flag in the LOCAL
-// buffer and stages rank w's payload.  All ranks add the staged payloads in rank order 0..W-1: the result is
-// bit-identical on every rank and deterministic.
+// buffer over NVLink as 8-byte words {value, sequence number} — one aligned 8-byte store each, so a word arrives whole and
+// carries its own flag: no fence, no separate flag store, ONE NVLink traversal on the critical path (the scheme of NCCL's
+// low-latency protocol; the first version stored the payload, fenced at system scope — a round trip — and then raised a
+// flag: +8 us per step at any world size).  Then the warp polls the words of rank w's slot in the LOCAL buffer until they
+// carry this call's number.  All ranks add the payloads in rank order 0..W-1: the result is bit-identical on every rank
+// and deterministic.
 //
-// Flags carry a sequence number kept in local device memory (incremented by the kernel itself, so a CUDA-graph replay
-// needs no new arguments); slots alternate by its parity, so a rank that runs ahead writes step k+1 into the other half
-// while a slow peer still reads step k (it cannot reach step k+2 before that peer has sent its step-k+1 flag, i.e. has
+// The sequence number lives in local device memory (incremented by the kernel itself, so a CUDA-graph replay needs no
+// new arguments); slots alternate by its parity, so a rank that runs ahead writes step k+1 into the other half while a
+// slow peer still reads step k (it cannot reach step k+2 before that peer has sent its step-k+1 words, i.e. has
 // finished reading step k).
 //
 // A peer that does not answer: ranks of a training job skew by seconds to minutes (checkpointing, validation on rank
@@ -22,8 +25,9 @@
 
 namespace sn {
 
-constexpr int kPeerSlotFloats = 128;              // 96 payload floats + flag, 512-byte slots
-constexpr int kPeerFlagIdx = kPeerSlotFloats - 1;
+constexpr int kPeerSlotFloats = 256;              // 1 KB slots: up to 128 words of {value, sequence number}
+constexpr int kPeerMaxPayload = SN_MAX_PARAM_PTRS;
+static_assert(2 * kPeerMaxPayload <= kPeerSlotFloats, "a slot holds the largest payload");
 constexpr int kPeerMaxWorld = 16;
 
 struct PeerArgs {
@@ -34,13 +38,14 @@ struct PeerArgs {
     long long timeout_ns;       // 0 = no bound
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_word_sys(float* p, float v, unsigned seq) {  // one 8-byte store: value + its flag
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ld_word_sys(const float* p, float& v, unsigned& seq) {
+    unsigned a, b;
+    asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    v = __uint_as_float(a);
+    seq = b;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -51,7 +56,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // data[0..n) <- sum over ranks, in place.  Call with ALL threads of a CTA of at least 32 * world threads; `data` must
 // be visible to the CTA (written before a __syncthreads() by its own threads, or by an earlier kernel).
 __device__ __forceinline__ void peer_exchange(const PeerArgs& a, float* __restrict__ data, int n) {
-    __shared__ float s_data[kPeerMaxWorld][kPeerSlotFloats];
+    __shared__ float s_data[kPeerMaxWorld][kPeerMaxPayload];
     __shared__ unsigned s_seq;
     __shared__ int s_bad;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,25 +72,25 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& a, float* __restri
     if (w < world) {
         // push: my payload -> rank w's buffer, slot [par][rank]
         float* dst = a.buf[w] + (size_t)(par * world + rank) * kPeerSlotFloats;
-        for (int i = lane; i < n; i += 32) dst[i] = data[i];
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) st_release_sys(reinterpret_cast<unsigned*>(dst + kPeerFlagIdx), seq);
-        // pull: wait for rank w's payload in MY buffer, slot [par][w]
+        for (int i = lane; i < n; i += 32) st_word_sys(dst + 2 * i, data[i], seq);
+        // pull: rank w's payload from MY buffer, slot [par][w]: every lane polls its own words
         const float* src = a.buf[rank] + (size_t)(par * world + w) * kPeerSlotFloats;
-        if (lane == 0) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned polls = 0;
-            while (ld_acquire_sys(reinterpret_cast<const unsigned*>(src + kPeerFlagIdx)) != seq) {
+        const unsigned long long t0 = global_timer_ns();
+        for (int i = lane; i < n; i += 32) {
+            float v;
+            unsigned got, polls = 0;
+            for (;;) {
+                ld_word_sys(src + 2 * i, v, got);
+                if (got == seq) break;
                 if ((++polls & 1023u) == 0u && a.timeout_ns > 0 && global_timer_ns() - t0 > (unsigned long long)a.timeout_ns) {
                     s_bad = 1;
+                    v = 0.f;
                     break;
                 }
-                __nanosleep(polls < 64u ? 20 : 200);
+                if (polls > 64u) __nanosleep(100);
             }
+            s_data[w][i] = v;
         }
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) s_data[w][i] = __ldcg(src + i);  // L2 (where the peer's stores land), not L1
     }
     __syncthreads();
     if (s_bad) {

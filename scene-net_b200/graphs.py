@@ -5,7 +5,7 @@ than what Python + autograd spend launching them: the eager module path is host-
 on static buffers is therefore captured once (our kernels are launched on torch's current
 stream, so `torch.cuda.graph` records them like any other) and replayed with one
 cudaGraphLaunch.  The graph contains: [H2D copy of x] -> (kernel synthesis || grid preparation) ->
-observer forward -> [criterion] -> G0 -> tap gradient (rows summed by its last CTA) -> parameter
+observer forward -> [criterion] -> G0 -> tap gradient -> row sum -> parameter
 Jacobian -> [gradient all-reduce] -> [D2H copy of the gradients].
 """
 from __future__ import annotations

@@ -261,7 +261,7 @@ def unpack_occupancy(bits: torch.Tensor, dtype: torch.dtype = torch.float32) -> 
 def prepare(x: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
     """One HBM pass over the grid batch: -> (x32, nnz).  x32 is the float32 copy the TMA-fed stencils read
     (x itself for float32 input), nnz the grid state buffer as an int64 device tensor ([0] = number of non-zero
-    voxels, [1] = ticket counter of the backward, then one occupancy bit per voxel): the forward and the backward use
+    voxels, [1] reserved, then one occupancy bit per voxel): the forward and the backward use
     the count ON THE DEVICE to pick the occupancy-driven kernels for sparse grids, and the occupancy-driven forward
     finds the non-zero voxels through the bits.
     stream: run the pass on this (side) stream after everything enqueued so far on the current one; the outputs

@@ -34,7 +34,9 @@ REPS = {"r1b": [("gpurun_out/prof_r1_step.ncu-rep", "r1b_ncu_step_kernels.csv"),
         # third part of the round: mask-driven occupancy forward (1.6 % and empty grids), scanning kernel before it, prepare with the bit mask
         "r1c": [("gpurun_out/prof_fo_r1h.ncu-rep", "r1c_ncu_fwd_occ.csv"), ("gpurun_out/prof_fo0_r1d.ncu-rep", "r1c_ncu_fwd_occ_empty_grids.csv"),
                 ("gpurun_out/prof_fs_r1c.ncu-rep", "r1c_ncu_fwd_scan_before.csv"), ("gpurun_out/prof_prep_r1h.ncu-rep", "r1c_ncu_prepare.csv")]}
-REPS["r2"] = [("gpurun_out/prof_fwd_r2j.ncu-rep", "r2_ncu_fwd_before_polish.csv"), ("gpurun_out/prof_fwd_r2n.ncu-rep", "r2_ncu_fwd_occ.csv")]
+REPS["r2"] = [("gpurun_out/prof_fwd_r2j.ncu-rep", "r2_ncu_fwd_before_polish.csv"), ("gpurun_out/prof_fwd_r2n.ncu-rep", "r2_ncu_fwd_occ.csv"),
+              ("gpurun_out/prof_tapgrad_r2.ncu-rep", "r2_ncu_tapgrad_bits.csv"), ("gpurun_out/r2s_fused.ncu-rep", "r2_ncu_fused_attempt_v4.csv"),
+              ("gpurun_out/r2s_ring.ncu-rep", "r2_ncu_ring_attempt.csv"), ("gpurun_out/r2v_vox.ncu-rep", "r2_ncu_voxelize_10M.csv")]
 for rep, name in REPS.get(tag, []):
     if not os.path.exists(rep):
         continue
@@ -68,7 +70,15 @@ if tag == "r2":
                               "algorithmic_bytes": 100663296,
                               "note": "x arrives as one occupancy bit per voxel from the state buffer (1 MB); pred (67 MB float64) is written "
                                       "through the 126 MB L2 and mostly still dirty there when the kernel ends"}}
-    for k in ("stencil_fwd_kernel", "tapgrad_sparse_kernel", "g0_kernel", "prepare_f64_kernel"):
+    for k in ("stencil_fwd_kernel", "g0_kernel", "prepare_f64_kernel"):
         new[k] = old[k]
+    # the tap gradient of binary grids (occupancy bits instead of the x tile): this round's capture
+    raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_tapgrad_r2.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, units = rr[0], rr[1]
+    row = rr[-1]
+    new["tapgrad_sparse_kernel"] = {"dram_bytes_read": val(row, "dram__bytes_read.sum"), "dram_bytes_write": val(row, "dram__bytes_write.sum"),
+                                    "algorithmic_bytes": 33554432 + 1048576,
+                                    "note": "binary grids: G0 (float32) + one occupancy bit per voxel; scratch/dbg_ring.py feeds a G0 tensor that is not L2-resident"}
     json.dump(new, open(f"{out}/r2_traffic.json", "w"), indent=1)
 print("ok", os.listdir(out))

@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu():
     assert lib.sn_criterion_workspace_bytes(0) == -1 and lib.sn_criterion_workspace_bytes(1 << 23) > 0
     assert lib.sn_criterion_fwd(None, None, 1, 8, None, None, 10, 1.0, 2.0, 1.0, 4.0, 1e-6, 3, None, None, None, 0, None) == -1
     assert lib.sn_param_penalty(None, None, 0, 5.0, None, None, None) == -1
-    assert lib.sn_peer_allreduce_buffer_bytes(8) == 2 * 8 * 128 * 4 and lib.sn_peer_allreduce_buffer_bytes(17) == -1
+    assert lib.sn_peer_allreduce_buffer_bytes(8) == 2 * 8 * 256 * 4 and lib.sn_peer_allreduce_buffer_bytes(17) == -1
     assert lib.sn_peer_allreduce(None, 13, 0, 2, None, None, None, 1000, None) == -1
     assert lib.sn_scenenet_param_grads_allreduce(None, None, None, None, None, 1.0, None, 0, 2, None, None, None, 1000, None) == -1
     # the selection rule of the AUTO modes (host-side query): config 2 at 1.6 % -> occupancy-driven forward and backward
