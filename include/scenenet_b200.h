@@ -28,7 +28,9 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 4
+/* v5: sn_vxg_to_xyz; the peer exchange moves {value, call number} words (sn_peer_allreduce_buffer_bytes doubled: every rank of a
+ * job must load the same library version); state[1] reserved (v4: ticket of the tap gradient's last-CTA reduction) */
+#define SN_ABI_VERSION 5
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define SN_OK 0

@@ -20,7 +20,7 @@ SN_MAX_PARAM_PTRS = 96
 SN_MAX_TAPS = 4096
 SN_CRIT_MAX_BINS = 12
 SN_CRIT_COEF = SN_CRIT_MAX_BINS + 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 KIND = {
     "cylinder_kernel": 0, "cylinderv2": 1, "cone_kernel": 2, "arrow": 3, "neg_sphere_kernel": 4, "negSpherev2": 5,
