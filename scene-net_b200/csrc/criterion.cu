@@ -133,7 +133,15 @@ __global__ void __launch_bounds__(1024) crit_finalize_kernel(const double* __res
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     for (int cc = c; cc < kCritRow; cc += 32) {
         double a = 0.0;
-        for (int r = g; r < rows; r += 32) a += partial[(size_t)r * kCritRow + cc];
+        // 8 independent loads in flight, then the adds in row order (one dependent load per add made this loop the kernel:
+        // 19 L2 round trips per thread)
+        for (int r0 = g; r0 < rows; r0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (r0 + 32 * i < rows) ? __ldcg(partial + (size_t)(r0 + 32 * i) * kCritRow + cc) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a += v[i];
+        }
         s_grp[g][cc] = a;
     }
     __syncthreads();
