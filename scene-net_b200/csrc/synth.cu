@@ -137,6 +137,28 @@ __device__ __forceinline__ double group_sum(double v, double* red, int group) {
     return s;
 }
 
+// N sums at once: the same per-value tree as group_sum (warp shuffles, then the warps in order) behind ONE pair of barriers
+template <int N>
+__device__ __forceinline__ void group_sum_vec(double (&v)[N], double* red /*[N][warps]*/, int group) {
+    constexpr int NW = kSynthThreads / 32;
+    const int w = (threadIdx.x % kSynthThreads) >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    group_sync(group);
+    if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) red[k * NW + w] = v[k];
+    }
+    group_sync(group);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) s += red[k * NW + i];
+        v[k] = s;
+    }
+}
+
 __device__ float lambda_eff_of(const SynthArgs& a, int g) {
     if (a.d.lambda_index[g] < 0) return 1.f;
     if (g != a.d.last_lambda) return *a.p[a.d.lambda_index[g]];
@@ -220,6 +242,70 @@ synth_fwd_kernel(const __grid_constant__ SynthArgs a, float* K, float* __restric
     }
 }
 
+// d raw_t / d parameter k of operator g (its alphabetical parameter list), before the zero-sum projection; v[k] = 0 for the
+// parameters tap t does not depend on
+__device__ __forceinline__ void tap_jacobian(int kind, const OpParams& o, bool plane, int t, int z, int kz, int kx, int ky,
+                                             double (&v)[5]) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = 0.0;
+    const double d2 = (double)tap_d2(plane, t, kz, kx, ky);
+    if (is_v2(kind)) {
+        const float radf = plane ? slice_shape(kind, o, z) : o.radius;
+        const double rp = (double)(radf + kEpsV2);
+        const double d4 = d2 * d2;
+        const double E = exp(-d4 / (2.0 * rp * rp));
+        const double sig = (double)o.sigma;
+        // raw = sigma*E (x -nf for the sphere); d raw/d rad = raw * d4 / rp^3
+        double draw_drad = sig * E * d4 / (rp * rp * rp);
+        double draw_dsig = E;
+        if (kind == SN_KIND_CYLINDER_V2) {
+            v[0] = draw_drad;
+            v[1] = draw_dsig;
+        } else if (kind == SN_KIND_NEGSPHERE_V2) {
+            const double nf = (double)o.neg_factor;
+            v[0] = (-sig * E);
+            v[1] = (-nf) * draw_drad;
+            v[2] = (-nf) * draw_dsig;
+        } else {  // arrow: apex, cone_inc, cone_radius, radius, sigma
+            v[4] = draw_dsig;
+            if (z >= o.ch) {
+                v[3] = draw_drad;
+            } else {
+                const bool open = (o.cone_inc >= 0.f) && (o.cone_inc <= 0.499f);  // clamp gate (arrow.py:244)
+                const float incc = fminf(fmaxf(o.cone_inc, 0.f), 0.499f);
+                const double tn = tan((double)(incc * kPiF));
+                const double h = (double)z;
+                v[2] = draw_drad * (h * tn);
+                if (open) v[1] = draw_drad * ((double)o.cone_radius * h * (double)kPiF * (1.0 + tn * tn));
+            }
+        }
+    } else {
+        const float sigf = plane ? slice_shape(kind, o, z) : o.sigma;
+        const double sg = (double)sigf, r = (double)o.radius;
+        const double u = d2 - r * r;
+        const double E = exp(-(u * u) / (2.0 * sg * sg));
+        const double draw_drad = E * 2.0 * u * r / (sg * sg);
+        const double draw_dsig = E * (u * u) / (sg * sg * sg);
+        if (kind == SN_KIND_CYLINDER_V1) {
+            v[0] = draw_drad;
+            v[1] = draw_dsig;
+        } else if (kind == SN_KIND_NEGSPHERE_V1) {
+            v[1] = draw_drad;
+            v[2] = draw_dsig;
+        } else {  // cone v1
+            v[3] = draw_drad;
+            if (z >= o.ch) {
+                v[4] = draw_dsig;
+            } else {
+                const int h = o.ch - 1 - z;
+                const double ang = (double)((o.cone_inc * kPiF) / (float)(2 + h));
+                v[2] = draw_dsig * sin(ang);
+                v[1] = draw_dsig * ((double)o.cone_radius * cos(ang) * (double)kPiF / (double)(2 + h));
+            }
+        }
+    }
+}
+
 // =====================================================================================
 // Backward.  MODE 0: dK given [G,T] (double).  MODE 1: dK_g = lambda_eff[g] * W (observer),
 // plus dlambda_g = <K_g - K_last, W>.
@@ -233,8 +319,9 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
                  const float* __restrict__ lambda_eff, const double* __restrict__ W, double scale,
                  float* __restrict__ dparams, const __grid_constant__ PeerArgs peer) {
     constexpr bool kObserver = MODE >= 1;
+    extern __shared__ double s_W[];  // observer modes: the tap gradient, loaded ONCE (it is read by three dependent phases)
     __shared__ double s_mean_all[kSynthGroups][64];
-    __shared__ double s_red_all[kSynthGroups][kSynthThreads / 32];
+    __shared__ double s_red_all[kSynthGroups][6 * (kSynthThreads / 32)];
     const int kz = a.d.kz, kx = a.d.kx, ky = a.d.ky, P = kx * ky, T = kz * P;
     const int group = threadIdx.x / kSynthThreads, ngroups = blockDim.x / kSynthThreads;
     const int tid = threadIdx.x % kSynthThreads, warp = tid >> 5, lane = tid & 31;  // tid: within the group
@@ -242,6 +329,8 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
     double* s_red = s_red_all[group];
 
     for (int i = threadIdx.x; i < a.d.n_param_ptrs; i += blockDim.x) dparams[i] = 0.f;
+    if (kObserver)
+        for (int t = threadIdx.x; t < T; t += blockDim.x) s_W[t] = W[t];
     __syncthreads();
 
     for (int g = group; g < a.d.n_geneos; g += ngroups) {
@@ -249,7 +338,7 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
         const OpParams o = load_op(a, g);
         const bool plane = is_plane_kind(kind);
         const double lam = kObserver ? (double)lambda_eff[g] : 1.0;
-        auto dk = [&](int t) -> double { return kObserver ? lam * W[t] : dK[(size_t)g * T + t]; };
+        auto dk = [&](int t) -> double { return kObserver ? lam * s_W[t] : dK[(size_t)g * T + t]; };
 
         // projection D = dK - mean(dK) over the zero-sum group (slice or whole volume)
         double vol_mean = 0.0;
@@ -267,86 +356,33 @@ synth_bwd_kernel(const __grid_constant__ SynthArgs a, const double* __restrict__
             vol_mean = group_sum(s, s_red, group) / (double)T;
         }
 
-        double acc[5] = {0, 0, 0, 0, 0};  // indexed like the operator's alphabetical parameter list
+        // acc[0..5): indexed like the operator's alphabetical parameter list; acc[5]: <K_g - K_last, W> (SCENE_Net.py:329-335)
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const bool want_lambda = kObserver && a.d.lambda_index[g] >= 0 && g != a.d.last_lambda;
+        const int last = a.d.last_lambda;
         for (int t = tid; t < T; t += kSynthThreads) {
             const int z = t / P;
             const double D = dk(t) - (plane ? s_mean[z] : vol_mean);
-            const double d2 = (double)tap_d2(plane, t, kz, kx, ky);
-            if (is_v2(kind)) {
-                const float radf = plane ? slice_shape(kind, o, z) : o.radius;
-                const double rp = (double)(radf + kEpsV2);
-                const double d4 = d2 * d2;
-                const double E = exp(-d4 / (2.0 * rp * rp));
-                const double sig = (double)o.sigma;
-                // raw = sigma*E (x -nf for the sphere); d raw/d rad = raw * d4 / rp^3
-                double draw_drad = sig * E * d4 / (rp * rp * rp);
-                double draw_dsig = E;
-                if (kind == SN_KIND_CYLINDER_V2) {
-                    acc[0] += D * draw_drad;
-                    acc[1] += D * draw_dsig;
-                } else if (kind == SN_KIND_NEGSPHERE_V2) {
-                    const double nf = (double)o.neg_factor;
-                    acc[0] += D * (-sig * E);
-                    acc[1] += D * (-nf) * draw_drad;
-                    acc[2] += D * (-nf) * draw_dsig;
-                } else {  // arrow: apex, cone_inc, cone_radius, radius, sigma
-                    acc[4] += D * draw_dsig;
-                    if (z >= o.ch) {
-                        acc[3] += D * draw_drad;
-                    } else {
-                        const bool open = (o.cone_inc >= 0.f) && (o.cone_inc <= 0.499f);  // clamp gate (arrow.py:244)
-                        const float incc = fminf(fmaxf(o.cone_inc, 0.f), 0.499f);
-                        const double tn = tan((double)(incc * kPiF));
-                        const double h = (double)z;
-                        acc[2] += D * draw_drad * (h * tn);
-                        if (open) acc[1] += D * draw_drad * ((double)o.cone_radius * h * (double)kPiF * (1.0 + tn * tn));
-                    }
-                }
-            } else {
-                const float sigf = plane ? slice_shape(kind, o, z) : o.sigma;
-                const double sg = (double)sigf, r = (double)o.radius;
-                const double u = d2 - r * r;
-                const double E = exp(-(u * u) / (2.0 * sg * sg));
-                const double draw_drad = E * 2.0 * u * r / (sg * sg);
-                const double draw_dsig = E * (u * u) / (sg * sg * sg);
-                if (kind == SN_KIND_CYLINDER_V1) {
-                    acc[0] += D * draw_drad;
-                    acc[1] += D * draw_dsig;
-                } else if (kind == SN_KIND_NEGSPHERE_V1) {
-                    acc[1] += D * draw_drad;
-                    acc[2] += D * draw_dsig;
-                } else {  // cone v1
-                    acc[3] += D * draw_drad;
-                    if (z >= o.ch) {
-                        acc[4] += D * draw_dsig;
-                    } else {
-                        const int h = o.ch - 1 - z;
-                        const double ang = (double)((o.cone_inc * kPiF) / (float)(2 + h));
-                        acc[2] += D * draw_dsig * sin(ang);
-                        acc[1] += D * draw_dsig * ((double)o.cone_radius * cos(ang) * (double)kPiF / (double)(2 + h));
-                    }
-                }
-            }
-        }
-        const int np = n_params_of(kind);
-        for (int k = 0; k < np; ++k) {
-            double s = group_sum(acc[k], s_red, group);
-            if (kind == SN_KIND_NEGSPHERE_V2 && k == 0) s += -vol_mean;             // direct -nf/T term
-            if (kind == SN_KIND_NEGSPHERE_V1 && k == 0) s += -vol_mean * (double)T;  // direct -nf term
-            if (tid == 0) dparams[a.d.param_index[g] + k] = (float)(s * scale);
-        }
-
-        if (kObserver && a.d.lambda_index[g] >= 0 && g != a.d.last_lambda) {
-            // dL/dlambda_g = <K_g, W> - <K_last, W>   (SCENE_Net.py:329-335)
-            const int last = a.d.last_lambda;
-            double s = 0.0;
-            for (int t = tid; t < T; t += kSynthThreads) {
+            double v[5];
+            tap_jacobian(kind, o, plane, t, z, kz, kx, ky, v);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[k] += D * v[k];
+            if (want_lambda) {
                 double kd = (double)K[(size_t)g * T + t];
                 if (last >= 0) kd -= (double)K[(size_t)last * T + t];
-                s += kd * W[t];
+                acc[5] += kd * s_W[t];
             }
-            s = group_sum(s, s_red, group);
-            if (tid == 0) dparams[a.d.lambda_index[g]] = (float)(s * scale);
+        }
+        group_sum_vec<6>(acc, s_red, group);
+        const int np = n_params_of(kind);
+        if (tid == 0) {
+            for (int k = 0; k < np; ++k) {
+                double s = acc[k];
+                if (kind == SN_KIND_NEGSPHERE_V2 && k == 0) s += -vol_mean;             // direct -nf/T term
+                if (kind == SN_KIND_NEGSPHERE_V1 && k == 0) s += -vol_mean * (double)T;  // direct -nf term
+                dparams[a.d.param_index[g] + k] = (float)(s * scale);
+            }
+            if (want_lambda) dparams[a.d.lambda_index[g]] = (float)(acc[5] * scale);
         }
         group_sync(group);
     }
@@ -427,7 +463,8 @@ extern "C" int sn_scenenet_param_grads(const sn_model_desc* desc, const float* c
     sn::SynthArgs a;
     sn::fill_args(a, desc, param_ptrs_host);
     const int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
-    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, sn::PeerArgs{});
+    const size_t smem = (size_t)desc->kz * desc->kx * desc->ky * sizeof(double);  // <= SN_MAX_TAPS * 8 = 32 KB
+    sn::synth_bwd_kernel<1><<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, sn::PeerArgs{});
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
@@ -447,7 +484,8 @@ extern "C" int sn_scenenet_param_grads_allreduce(const sn_model_desc* desc, cons
     // the exchange needs one warp per rank: at least 32 * world threads
     int groups = desc->n_geneos < sn::kSynthGroups ? desc->n_geneos : sn::kSynthGroups;
     while (sn::kSynthThreads * groups < 32 * world) ++groups;
-    sn::synth_bwd_kernel<2><<<1, sn::kSynthThreads * groups, 0, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, peer);
+    const size_t smem = (size_t)desc->kz * desc->kx * desc->ky * sizeof(double);
+    sn::synth_bwd_kernel<2><<<1, sn::kSynthThreads * groups, smem, (cudaStream_t)stream>>>(a, nullptr, K, lambda_eff, W, scale, dparams, peer);
     SN_LAUNCH_CHECK();
     return SN_OK;
 }
