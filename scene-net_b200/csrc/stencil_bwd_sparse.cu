@@ -18,6 +18,10 @@
 // Which kernel runs (this one or the dense stencil) is decided ON THE DEVICE from the non-zero count written by
 // sn_grid_prepare: both are launched, the one that is not selected returns at once — no host synchronisation,
 // CUDA-graph friendly.
+//
+// Round 2: with the grid state buffer and a BINARY grid (state[4] == 0: every non-zero voxel is 1) the voxels come from the
+// occupancy bits of the state buffer — no x tile is staged or scanned, a stage is the G0 box alone (one more stage in
+// flight).  The kernel is bound by the ~3 us a TMA box takes to land times the stages in flight, not by bytes.
 #include <stdlib.h>
 #include <map>
 #include <mutex>
