@@ -84,7 +84,7 @@ def test_device_side_selection(density, expect_sparse):
         Wo = ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_DENSE if expect_sparse else SN_TAPGRAD_SPARSE)
         assert torch.equal(Wa, We)
         assert torch.allclose(Wa, Wo, rtol=1e-4, atol=1e-4 * float(Wo.abs().max()))
-        # the same count buffer serves a second backward (the last CTA resets its ticket)
+        # the same state buffer serves a second backward (the kernels leave its counters untouched)
         assert torch.equal(ops.tapgrad(x32, g0, ks, nnz=nnz, mode=SN_TAPGRAD_AUTO), We)
     # no count -> dense
     assert torch.equal(ops.tapgrad(x, g0, ks), ops.tapgrad(x, g0, ks, mode=SN_TAPGRAD_DENSE))
@@ -137,7 +137,7 @@ def test_bwd_entry_point_equals_g0_plus_tapgrad(B, grid, ks, density, binary, dt
     tol = 2e-6 * _ref_tapgrad(x.abs(), g0.abs(), ks) + 1e-12
     Wf = ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_SPARSE)
     assert bool(((Wf - ref).abs() <= tol).all()), f"max err {(Wf - ref).abs().max():.3e}"
-    # deterministic, and the state buffer serves a second backward (the last CTA resets the ticket)
+    # deterministic, and the state buffer serves a second backward
     assert torch.equal(Wf, ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_SPARSE))
     # device-side choice: the occupancy-driven kernel below the occupancy threshold, the dense stencil above it
     Wa = ops.scenenet_bwd(x32, pred, dpred, ks, nnz=state, mode=SN_TAPGRAD_AUTO)
